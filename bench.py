@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the fused segmentation loss + metric path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg5] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (K1: softmax-CE fwd+bwd + argmax + confusion matrix, preceded by
+the K4 label pre-pass when class weights / ignore_index make Σw data dependent) over one batch of
+synthetic tiles per GPU.  Rank 0 prints ONE JSON line.
+
+  value     whole-job Gpixel/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  roofline  the dominant kernel (K1): algorithmic bytes per launch / its average launch duration
+            (events around every launch inside the timed region) against MEASURED_PEAKS.json
+  e2e       the same metric through the host-buffer C-ABI call (cvcs_host_ce_fused): pinned host
+            logits + labels copied in, loss + confusion matrix read back, every step
+  cpu_baseline   the reference's own CPU path (oracle/torch_path.py: the torch calls the reference
+            makes) timed on this box's host cores on a bounded sample (rank 0, N=1)
+  --impl reference   that CPU path as the measured arm (no GPU work at all)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gpixel/s fused seg loss+metric"
+UNIT = "Gpixel/s"
+
+WORKLOADS = {
+    # name: per-GPU batch, classes, H, W, logits dtype, weights, ignore_index, label dtype
+    "cfg2": dict(B=16, C=7, H=1024, W=1024, dtype="f32", weighted=False, ignore_index=-100,
+                 desc="1xB200: fused softmax-CE fwd+bwd + argmax + confusion matrix, batch 16 of 1024x1024, 7 classes, fp32 logits"),
+    "cfg3": dict(B=16, C=7, H=1024, W=1024, dtype="bf16", weighted=True, ignore_index=255,
+                 desc="same path with bf16 logits, class weights and ignore_index=255 (LoveDA-style labels)"),
+    "cfg5": dict(B=16, C=20, H=1024, W=1024, dtype="f32", weighted=False, ignore_index=-100,
+                 desc="20-class head, fp32 logits (the cfg5 head at batch 16 per GPU)"),
+}
+
+
+def algorithmic_bytes_per_pixel(C: int, esize: int, grad: bool = True) -> int:
+    """read logits + write dlogits + read label (u8) + write argmax (u8)."""
+    return C * esize * (2 if grad else 1) + 2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(workload: str):
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, ~5 ms period)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons = index, [], set()
+        self.max_mhz, self._stop, self._t, self.ok = None, threading.Event(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    _NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+              0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self._NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.ok:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t is not None:
+            self._stop.set()
+            self._t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def synth_inputs(torch, wl, dev, seed, n_sets):
+    """Seeded synthetic logits (randn*3) and blocky labels (32x32 constant blocks, real masks have
+    long runs); cfg3 adds 10% ignore pixels and histogram-derived class weights."""
+    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
+    dt = torch.float32 if wl["dtype"] == "f32" else torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(seed)
+    sets = []
+    for _ in range(n_sets):
+        x = (torch.randn(B, C, H, W, generator=g, device=dev, dtype=torch.float32) * 3).to(dt)
+        t = torch.randint(0, C, (B, H // 32, W // 32), generator=g, device=dev, dtype=torch.uint8)
+        t = t.repeat_interleave(32, 1).repeat_interleave(32, 2).contiguous()
+        if wl["ignore_index"] == 255:
+            t[torch.rand(B, H, W, generator=g, device=dev) < 0.1] = 255
+        sets.append((x, t))
+    weight = None
+    if wl["weighted"]:
+        counts = torch.bincount(sets[0][1][sets[0][1] != 255].flatten().long(), minlength=C).float()
+        weight = (counts.sum() / (C * counts.clamp(min=1))).to(torch.float32)
+    return sets, weight
+
+
+def cpu_reference_rate(wl, steps, warmup, budget_s, log=None):
+    """Times the reference's CPU path (oracle/torch_path.hot_path_step) on a bounded sample of the
+    workload.  Returns (Gpixel/s, seconds per step, sample description, cores)."""
+    import torch
+    from oracle import torch_path
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    C, W = wl["C"], wl["W"]
+    g = torch.Generator().manual_seed(0)
+
+    def make(rows, tiles):
+        x = torch.randn(tiles, C, rows, W, generator=g) * 3
+        if wl["dtype"] == "bf16":
+            x = x.to(torch.bfloat16).float()   # torch rejects fp32 weights with bf16 logits: fp32 on the same values
+        t = torch.randint(0, C, (tiles, max(rows // 32, 1), W // 32), generator=g, dtype=torch.uint8)
+        t = t.repeat_interleave(32, 1).repeat_interleave(32, 2)[:, :rows].contiguous()
+        if wl["ignore_index"] == 255:
+            t[torch.rand(tiles, rows, W, generator=g) < 0.1] = 255
+        w = (torch.rand(C, generator=g) + 0.5) if wl["weighted"] else None
+        return x, t, w
+
+    def one(x, t, w):
+        t0 = time.perf_counter()
+        torch_path.hot_path_step(x, t, w, wl["ignore_index"], C, ignore_background_eval=False)
+        return time.perf_counter() - t0
+
+    # calibrate on a 128-row strip, then size the per-step sample to the time budget
+    x, t, w = make(128, 1)
+    one(x, t, w)
+    per_px = min(one(x, t, w) for _ in range(2)) / (128 * W)
+    px_budget = budget_s / max(steps + warmup, 1) / per_px
+    rows = int(min(wl["H"], max(32, (px_budget // W) // 32 * 32)))
+    tiles = int(min(2, max(1, px_budget // (rows * W)))) if rows == wl["H"] else 1
+    x, t, w = make(rows, tiles)
+    for _ in range(warmup):
+        one(x, t, w)
+    times = [one(x, t, w) for _ in range(steps)]
+    sec = sum(times) / len(times)
+    px = tiles * rows * W
+    sample = f"{tiles} tile(s) of {rows}x{W} px, {C} classes per step ({px} px); {steps} steps after {warmup} warm-up"
+    return px / sec / 1e9, sec, sample, cores
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, sec, sample, cores = cpu_reference_rate(wl, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']} — reference CPU path (torch CPU calls as at "
+                               "utils.py:230,90,93-94; train.py:122-125) on a bounded sample", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
+    ap.add_argument("--path", default="auto", choices=["auto", "tma", "direct", "generic"])
+    ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--label-dtype", default="u8", choices=["u8", "i64"])
+    ap.add_argument("--no-grad", action="store_true", help="forward/eval only (no dlogits)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["B"] = args.batch
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cvcs_b200 import _lib, ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (cvcs_b200 has no CPU path; use --impl reference for the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    _lib.set_option(_lib.OPT_CE_PATH, {"auto": 0, "tma": 1, "direct": 2, "generic": 3}[args.path])
+    _lib.set_option(_lib.OPT_TMA_STAGES, args.stages)
+
+    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
+    esize = 4 if wl["dtype"] == "f32" else 2
+    px_per_gpu = B * H * W
+    grad = not args.no_grad
+    n_sets = 3   # rotate buffer sets; each set (logits + dlogits) is far larger than the 126 MB L2 anyway
+    sets, weight = synth_inputs(torch, wl, dev, seed=1234 + rank, n_sets=n_sets)
+    if args.label_dtype == "i64":
+        sets = [(x, t.long()) for x, t in sets]
+    dl = [torch.empty_like(x) for x, _ in sets] if grad else [None] * n_sets
+    am = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in sets]
+    confmat = torch.zeros((C, C), dtype=torch.int64, device=dev)
+    loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
+    sums = torch.zeros(3, dtype=torch.float64, device=dev)
+    tw = torch.zeros(2, dtype=torch.float64, device=dev)
+    hist = torch.zeros(C + 2, dtype=torch.int64, device=dev)
+    ii = wl["ignore_index"]
+    data_dependent_tw = wl["weighted"] or (0 <= ii <= 255) or args.label_dtype == "i64"
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    sums_comm = torch.zeros(3, dtype=torch.float64, device=dev)
+    launches = {"n": 0}
+    k1_events = []
+
+    def step(i, timed):
+        x, t = sets[i % n_sets]
+        inv, inv_dev = 0.0, None
+        if grad:
+            if data_dependent_tw:
+                # K4 pre-pass: Σ v·w[y] must be known before the first dlogit is written
+                if world > 1:
+                    hist.zero_()
+                    ops.label_hist(t, C, ii, hist=hist)
+                    dist.all_reduce(hist)                       # global Σw: results equal the 1-process run
+                    ops.total_weight(hist, weight, C, ii, out=tw)
+                    launches["n"] += 2
+                else:
+                    ops.label_hist(t, C, ii, weight=weight, total_weight_out=tw)
+                    launches["n"] += 1
+                inv_dev = tw[1:]
+            else:
+                inv = 1.0 / float(px_per_gpu * world)           # nothing can be ignored: Σw = global pixel count
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        ops.ce_fused(x, t, weight, ii, want_grad=grad, inv_total_weight=inv, inv_total_weight_dev=inv_dev,
+                     dlogits=dl[i % n_sets], argmax=am[i % n_sets], confmat=confmat, loss_sums=sums, loss_out=loss_out)
+        launches["n"] += 1
+        if timed:
+            e1.record()
+            k1_events.append((e0, e1))
+        if world > 1:
+            # global loss of this step: f64[3] all-reduce on a side stream, overlapped with the next K1
+            ev = torch.cuda.Event()
+            ev.record()
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                sums_comm.copy_(sums)
+                dist.all_reduce(sums_comm)
+
+    def fence():
+        if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(side)
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i, False)
+    fence()
+    confmat.zero_()
+    launches["n"] = 0
+    sampler = ClockSampler(local)
+    sampler.start()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        step(i, True)
+    if world > 1:
+        torch.cuda.current_stream(dev).wait_stream(side)
+        dist.all_reduce(confmat)                                # one C*C all-reduce per pass
+    end.record()
+    fence()
+    sampler.stop()
+    ms_total = start.elapsed_time(end)
+    k1_ms = [a.elapsed_time(b) for a, b in k1_events]
+    if world > 1:
+        tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax.item())
+    ms_per_step = ms_total / args.steps
+    value = world * px_per_gpu / (ms_per_step * 1e-3) / 1e9
+    gpu_launches = launches["n"]
+    total_cm = int(confmat.sum().item())
+
+    # ---- roofline of the dominant kernel (K1) -----------------------------------------------------
+    peak, peak_src = load_peaks()
+    bpp = algorithmic_bytes_per_pixel(C, esize, grad)
+    k1_avg_ms = sum(k1_ms) / len(k1_ms)
+    achieved = bpp * px_per_gpu / (k1_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": load_traffic(args.workload), "kernel": "cvcs K1 ce_fused", "bytes_per_pixel": bpp,
+                "pixels_per_launch": px_per_gpu, "avg_launch_ms": k1_avg_ms, "peak_source": peak_src,
+                "frac_of_8TBps_nominal": achieved / 8000.0}
+
+    # ---- e2e through the host-buffer C-ABI call ----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        x0, t0 = sets[0]
+        hx = torch.empty(x0.shape, dtype=x0.dtype, pin_memory=True)
+        ht = torch.empty(t0.shape, dtype=t0.dtype, pin_memory=True)
+        hx.copy_(x0)
+        ht.copy_(t0)
+        hw = None if weight is None else weight.cpu()
+        hcm = torch.zeros((C, C), dtype=torch.int64)
+        ctx = ops.HostContext(local, px_per_gpu, C, x0.dtype)
+        for _ in range(2):
+            ctx.ce_fused(hx, ht, hw, ii, want_grad=grad, confmat=hcm)
+        fence()
+        t_0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            l_e2e, _ = ctx.ce_fused(hx, ht, hw, ii, want_grad=grad, confmat=hcm)   # returns with results on the host
+        dt = time.perf_counter() - t_0
+        if world > 1:
+            tm = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dt = float(tm.item())
+        ctx.close()
+        e2e = {"value": world * px_per_gpu * args.e2e_steps / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": hx.numel() * hx.element_size() + ht.numel() * ht.element_size()
+               + (0 if hw is None else hw.numel() * 4),
+               "d2h_bytes_per_step": C * C * 8 + 3 * 8 * min(B, 64),
+               "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "api": "cvcs_host_ce_fused (pinned host logits+labels in; loss + confusion matrix out; dlogits/argmax stay "
+                      "on the device for the model backward)"}
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, sec, sample, cores = cpu_reference_rate(wl, steps=3, warmup=1, budget_s=20.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": wl["dtype"], "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "per_gpu_batch": B, "classes": C,
+                       "tile": [H, W], "labels": args.label_dtype + " (blocky 32x32)", "grad": grad,
+                       "l2": f"inputs larger than L2: {n_sets} rotating sets of {px_per_gpu * C * esize * (2 if grad else 1) / 1e6:.0f} MB",
+                       "parallelism": f"dp{world}: tiles sharded per GPU; f64[3] loss all-reduce per step (side stream) + "
+                                      "one CxC confusion all-reduce per pass" if world > 1 else "single GPU",
+                       "k4_prepass": bool(grad and data_dependent_tw), "path": args.path},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+            "clocks": sampler.summary(),
+            "check": {"confusion_total": total_cm, "loss": float(loss_out.item())},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,236 @@
+// ce_common.cuh — device code shared by the K1 variants (direct-load and TMA-staged):
+// the per-pixel softmax-CE / gradient / argmax arithmetic and the deterministic loss epilogue.
+//   loss   = Σ v w[y] (lse(x) - x[y]) / Σ v w[y]        nn.CrossEntropyLoss(weight, ignore_index),
+//                                                        reference utils.py:223-242, train.py:122
+//   dlogit = v w[y] (softmax(x) - onehot(y)) / Σ v w[y]  loss.backward(), train.py:125
+//   argmax = first maximal class, NaN is maximal         torch.max(y_pred, dim=0), utils.py:90
+#pragma once
+#include "common.cuh"
+
+namespace cvcs {
+
+struct CeParams {
+    const void* logits;
+    const void* target;
+    const float* weight;
+    void* dlogits;
+    void* argmax;
+    unsigned long long* confmat;
+    const double* inv_tw_dev;
+    double inv_tw;
+    double* loss_sums;
+    float* loss_out;
+    Workspace* ws;
+    long long ignore_index;
+    long long hw;                  // pixels per image
+    long long n_pixels;            // B * hw
+    long long n_items;             // direct: B*hw/VEC work items; tma: number of chunks
+    unsigned int items_per_image;  // direct: hw/VEC; tma (NCHW): chunks per image
+    int C;
+    int target_i64;  // 0: u8, 1: i64
+    int argmax_i64;  // 0: u8, 1: i64
+};
+
+// launchers (one translation unit each)
+int ce_direct_launch(const CeParams& p, int logits_dtype, int vec, cudaStream_t stream, bool* handled);
+int ce_tma_launch(const CeParams& p, int logits_dtype, int layout, cudaStream_t stream, bool* handled);
+int ce_generic_launch(const CeParams& p, int logits_dtype, int layout, cudaStream_t stream);
+
+constexpr int kPrivBinsMax = 64;  // C*C <= 64 -> per-thread private u16 counters
+constexpr int kMaxRegC = 21;      // largest C with register-resident instantiations
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ int ignore_as_int_u8(long long ignore_index) {
+    return (ignore_index >= 0 && ignore_index <= 255) ? static_cast<int>(ignore_index) : -1000;
+}
+
+// Label encoding used by all K1 kernels: [0,C) valid class, -1 ignored, anything else
+// (>= C or -2) out of bounds.
+template <int VEC>
+__device__ __forceinline__ void decode_labels_u8(const uint32_t* words, long long ignore_index, int (&t)[VEC]) {
+    const int ign = ignore_as_int_u8(ignore_index);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int v = (words[i / 4] >> (8 * (i % 4))) & 0xff;
+        t[i] = (v == ign) ? -1 : v;
+    }
+}
+__device__ __forceinline__ int decode_label_i64(uint32_t lo, uint32_t hi, long long ignore_index) {
+    const long long a = (static_cast<long long>(hi) << 32) | lo;
+    return a == ignore_index ? -1 : ((a < 0 || a > 0x7fffffff) ? -2 : static_cast<int>(a));
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_targets(const CeParams& p, long long pix, int (&t)[VEC]) {
+    if (p.target_i64) {
+        load_labels_i64<VEC>(reinterpret_cast<const long long*>(p.target) + pix, p.ignore_index, -1, t);
+    } else {
+        load_labels_u8<VEC>(reinterpret_cast<const uint8_t*>(p.target) + pix, t);
+        const int ign = ignore_as_int_u8(p.ignore_index);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) t[i] = (t[i] == ign) ? -1 : t[i];
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_argmax(const CeParams& p, long long pix, const int (&a)[VEC]) {
+    if (p.argmax_i64) {
+        long long* out = reinterpret_cast<long long*>(p.argmax) + pix;
+        if constexpr (VEC % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < VEC / 2; ++i) {
+                Raw<16> r;
+                r.v = make_uint4(static_cast<uint32_t>(a[2 * i]), 0u, static_cast<uint32_t>(a[2 * i + 1]), 0u);
+                r.store(out + 2 * i);
+            }
+        } else {
+            Raw<8> r;
+            r.v = make_uint2(static_cast<uint32_t>(a[0]), 0u);
+            r.store(out);
+        }
+    } else {
+        uint8_t* out = reinterpret_cast<uint8_t*>(p.argmax) + pix;
+        if constexpr (VEC == 1) {
+            Raw<1> r;
+            r.v = static_cast<uint8_t>(a[0]);
+            r.store(out);
+        } else if constexpr (VEC == 2) {
+            Raw<2> r;
+            r.v = static_cast<uint16_t>(a[0] | (a[1] << 8));
+            r.store(out);
+        } else {
+            Raw<VEC> r;
+#pragma unroll
+            for (int i = 0; i < VEC / 4; ++i)
+                r.word(i) = static_cast<uint32_t>(a[4 * i]) | (static_cast<uint32_t>(a[4 * i + 1]) << 8) |
+                            (static_cast<uint32_t>(a[4 * i + 2]) << 16) | (static_cast<uint32_t>(a[4 * i + 3]) << 24);
+            r.store(out);
+        }
+    }
+}
+
+// One pixel: x[0..C) holds the logits on entry and (if do_grad) the gradients on exit.
+// Returns the argmax; accumulates the loss terms.  tv uses the label encoding above.
+template <int C>
+__device__ __forceinline__ int pixel_ce(float (&x)[C], int tv, const float* __restrict__ wsm, float inv_tw,
+                                        bool do_grad, float& step_l, float& step_w, unsigned int& bad) {
+    float best = x[0], m = x[0];
+    int arg = 0;
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+        if (better(x[c], best)) {
+            best = x[c];
+            arg = c;
+        }
+        m = fmaxf(m, x[c]);
+    }
+    const bool valid = static_cast<unsigned int>(tv) < static_cast<unsigned int>(C);
+    bad += (!valid && tv != -1) ? 1u : 0u;
+    float xt = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) xt = (c == tv) ? x[c] : xt;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        x[c] = exp2f((x[c] - m) * kLog2e);
+        s += x[c];
+    }
+    const float w = valid ? wsm[tv] : 0.f;
+    const float nll = (m - xt) + __logf(s);
+    step_l += valid ? w * nll : 0.f;
+    step_w += w;
+    if (do_grad) {
+        const float gsc = w * inv_tw;  // 0 at ignored pixels -> exact zeros, as autograd gives
+        const float r = __fdividef(gsc, s);
+#pragma unroll
+        for (int c = 0; c < C; ++c) x[c] = fmaf(x[c], r, (c == tv) ? -gsc : 0.f);
+    }
+    return arg;
+}
+
+// Block-reduce {Σ w·nll, Σ w}; the last CTA folds the per-block fp64 partials in a fixed
+// order -> bit-stable run to run, no float atomics.  Must be called by all NWARPS*32 threads.
+template <int NWARPS>
+__device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, double wsum, unsigned int bad) {
+    __shared__ double red[2 * NWARPS];
+    __shared__ unsigned int is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    lsum = warp_sum(lsum);
+    wsum = warp_sum(wsum);
+    bad = warp_sum(bad);
+    if (lane == 0) {
+        red[warp] = lsum;
+        red[NWARPS + warp] = wsum;
+        if (bad) atomicAdd(&p.ws->bad, static_cast<unsigned long long>(bad));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) {
+            a += red[w];
+            b += red[NWARPS + w];
+        }
+        p.ws->partial[2 * blockIdx.x] = a;
+        p.ws->partial[2 * blockIdx.x + 1] = b;
+        __threadfence();
+        const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += NWARPS * 32) {
+        a += __ldcg(&p.ws->partial[2 * i]);
+        b += __ldcg(&p.ws->partial[2 * i + 1]);
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) {
+        red[warp] = a;
+        red[NWARPS + warp] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = 0.0;
+        b = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) {
+            a += red[w];
+            b += red[NWARPS + w];
+        }
+        const unsigned long long nbad = atomicAdd(&p.ws->bad, 0ull);
+        p.loss_sums[0] = a;
+        p.loss_sums[1] = b;
+        p.loss_sums[2] = static_cast<double>(nbad);
+        if (p.loss_out) {
+            float l = static_cast<float>(a / b);  // 0/0 -> NaN like torch (everything ignored)
+            if (nbad) l = __int_as_float(0x7fc00000);
+            *p.loss_out = l;
+        }
+        p.ws->bad = 0ull;
+        p.ws->ticket = 0u;
+        __threadfence();
+    }
+}
+
+#endif  // __CUDACC__
+
+// persistent grid = resident CTAs per SM x SMs
+template <typename K>
+int persistent_grid(K kernel, int threads, int smem_bytes, int* grid_out) {
+    int per_sm = 0;
+    if (smem_bytes > 48 * 1024)
+        CVCS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CVCS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes));
+    if (per_sm < 1) return set_error(CVCS_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %d B)", smem_bytes);
+    int g = per_sm * num_sms();
+    if (g > kMaxGrid) g = kMaxGrid;
+    *grid_out = g;
+    return CVCS_OK;
+}
+
+}  // namespace cvcs

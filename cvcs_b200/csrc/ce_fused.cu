@@ -1,0 +1,85 @@
+// ce_fused.cu — K1 entry: argument validation and variant selection.
+//   tma     : warp-specialised, cp.async.bulk-staged (ce_tma_impl.cuh) — primary path
+//   direct  : register-resident 128-bit LDG/STG, NCHW (ce_direct.cu)
+//   generic : any C <= 1024 / any layout, one pixel per thread (ce_direct.cu)
+// cvcs_set_option(CVCS_OPT_CE_PATH, ...) forces a variant for A/B measurements and path-coverage
+// tests (all are CUDA; there is no CPU path).
+#include <stdlib.h>
+#include <string.h>
+
+#include "ce_common.cuh"
+
+namespace cvcs {
+
+int ce_tma_launch_f32(const CeParams& p, int layout, cudaStream_t stream, bool* handled);
+int ce_tma_launch_bf16(const CeParams& p, int layout, cudaStream_t stream, bool* handled);
+
+int ce_fused_launch(const void* logits, int logits_dtype, int layout, const void* target, int target_dtype,
+                    const float* weight, long long ignore_index, int B, int C, int H, int W,
+                    double inv_total_weight, const double* inv_total_weight_dev, void* dlogits, void* argmax,
+                    int argmax_dtype, unsigned long long* confmat, double* loss_sums, float* loss_out,
+                    void* workspace, cudaStream_t stream) {
+    CVCS_REQUIRE(logits && target && loss_sums && workspace, "cvcs_ce_fused: NULL logits/target/loss_sums/workspace");
+    CVCS_REQUIRE(logits_dtype == CVCS_F32 || logits_dtype == CVCS_BF16, "cvcs_ce_fused: logits dtype tag %d (want f32/bf16)", logits_dtype);
+    CVCS_REQUIRE(layout == CVCS_NCHW || layout == CVCS_NHWC, "cvcs_ce_fused: layout %d", layout);
+    CVCS_REQUIRE(target_dtype == CVCS_U8 || target_dtype == CVCS_I64,
+                 "cvcs_ce_fused: expected target dtype Long (i64) or Byte (u8), got tag %d", target_dtype);
+    CVCS_REQUIRE(!argmax || argmax_dtype == CVCS_U8 || argmax_dtype == CVCS_I64, "cvcs_ce_fused: argmax dtype tag %d", argmax_dtype);
+    CVCS_REQUIRE(B > 0 && C >= 1 && H > 0 && W > 0, "cvcs_ce_fused: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+    if (C > 1024) return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_ce_fused: C=%d > 1024", C);
+    CVCS_REQUIRE(!(argmax && argmax_dtype == CVCS_U8 && C > 256), "cvcs_ce_fused: u8 argmax needs C <= 256");
+
+    const long long hw = static_cast<long long>(H) * W;
+    const long long n_pixels = hw * B;
+    CVCS_REQUIRE(n_pixels < (1ll << 33), "cvcs_ce_fused: too many pixels (%lld)", n_pixels);
+
+    CeParams p{};
+    p.logits = logits;
+    p.target = target;
+    p.weight = weight;
+    p.dlogits = dlogits;
+    p.argmax = argmax;
+    p.confmat = confmat;
+    p.inv_tw_dev = inv_total_weight_dev;
+    p.inv_tw = inv_total_weight;
+    p.loss_sums = loss_sums;
+    p.loss_out = loss_out;
+    p.ws = reinterpret_cast<Workspace*>(workspace);
+    p.ignore_index = ignore_index;
+    p.hw = hw;
+    p.n_pixels = n_pixels;
+    p.C = C;
+    p.target_i64 = target_dtype == CVCS_I64;
+    p.argmax_i64 = argmax_dtype == CVCS_I64;
+
+    const int forced = get_option(CVCS_OPT_CE_PATH);  // 0 auto, 1 tma, 2 direct, 3 generic
+    const int esize = logits_dtype == CVCS_F32 ? 4 : 2;
+    auto aligned = [](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
+    const bool ptr16 = aligned(logits, 16) && aligned(dlogits, 16) && aligned(target, 16) && aligned(argmax, 16);
+    bool handled = false;
+    int rc = CVCS_OK;
+
+    if (forced != 3 && C >= 2 && C <= kMaxRegC && ptr16) {
+        // ---- TMA-staged: every bulk copy must be a multiple of 16 bytes
+        const bool tma_ok = layout == CVCS_NCHW ? (hw % 16 == 0) : (n_pixels % 16 == 0);
+        if (tma_ok && forced != 2) {
+            rc = logits_dtype == CVCS_F32 ? ce_tma_launch_f32(p, layout, stream, &handled)
+                                          : ce_tma_launch_bf16(p, layout, stream, &handled);
+            if (handled) return rc;
+        }
+        // ---- direct NCHW: f32 4 pixels/thread; bf16 8 pixels/thread up to C=12, else 4
+        if (layout == CVCS_NCHW && forced != 1) {
+            const int vec = logits_dtype == CVCS_F32 ? 4 : (C <= 12 ? 8 : 4);
+            if (hw % vec == 0) {
+                p.n_items = n_pixels / vec;
+                p.items_per_image = static_cast<unsigned int>(hw / vec);
+                rc = ce_direct_launch(p, logits_dtype, vec, stream, &handled);
+                if (handled) return rc;
+            }
+        }
+    }
+    (void)esize;
+    return ce_generic_launch(p, logits_dtype, layout, stream);
+}
+
+}  // namespace cvcs

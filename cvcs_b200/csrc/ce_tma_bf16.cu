@@ -1,0 +1,17 @@
+// ce_tma_bf16.cu — bf16 instantiations of the TMA-staged K1 (see ce_tma_impl.cuh).
+// Arithmetic is fp32; gradients are rounded to bf16 once (round-to-nearest-even).
+#include "ce_tma_impl.cuh"
+
+namespace cvcs {
+
+int ce_tma_launch_bf16(const CeParams& p, int layout, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    if (layout == CVCS_NCHW) {
+        if (p.C <= 8) return tma::dispatch<__nv_bfloat16, 8, false, 2, 8>(p, stream, handled);
+        if (p.C <= 16) return tma::dispatch<__nv_bfloat16, 4, false, 9, 16>(p, stream, handled);
+        return tma::dispatch<__nv_bfloat16, 2, false, 17, kMaxRegC>(p, stream, handled);
+    }
+    return tma::dispatch<__nv_bfloat16, 8, true, 2, 12>(p, stream, handled);
+}
+
+}  // namespace cvcs

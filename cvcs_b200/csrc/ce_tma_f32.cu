@@ -1,0 +1,17 @@
+// ce_tma_f32.cu — fp32 instantiations of the TMA-staged K1 (see ce_tma_impl.cuh).
+#include "ce_tma_impl.cuh"
+
+namespace cvcs {
+
+// pixels per thread chosen so that one stage (C planes x 256*VECP pixels) stays <= 32 KB
+int ce_tma_launch_f32(const CeParams& p, int layout, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    if (layout == CVCS_NCHW) {
+        if (p.C <= 8) return tma::dispatch<float, 4, false, 2, 8>(p, stream, handled);
+        if (p.C <= 16) return tma::dispatch<float, 2, false, 9, 16>(p, stream, handled);
+        return tma::dispatch<float, 1, false, 17, kMaxRegC>(p, stream, handled);
+    }
+    return tma::dispatch<float, 4, true, 2, 12>(p, stream, handled);
+}
+
+}  // namespace cvcs

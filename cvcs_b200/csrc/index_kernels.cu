@@ -1,0 +1,553 @@
+// index_kernels.cu — the label / index-map kernels around K1:
+//   K4 label histogram (+ Σ w[y])   <- Loader._get_class_count, dataset.py:346-358; the 'mean'
+//                                       divisor of nn.CrossEntropyLoss (utils.py:230,238)
+//   K2 argmax over the class dim     <- torch.max / torch.argmax, utils.py:90,158,504; esa.py:56
+//   K3 confusion matrix from indices <- MulticlassConfusionMatrix.update, utils.py:93-94
+//   grad scaling                     <- autograd's grad_output * dlogits when grad_output != 1
+// All are byte/integer streaming kernels: HBM-bound, 128-bit coalesced loads, persistent grids,
+// shared-memory privatised bins flushed with one 64-bit global atomic per bin per CTA.
+#include "common.cuh"
+
+namespace cvcs {
+namespace {
+
+template <typename K>
+int grid_for(K kernel, int smem_bytes, long long blocks_needed, int* grid_out) {
+    int per_sm = 0;
+    if (smem_bytes > 48 * 1024)
+        CVCS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CVCS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem_bytes));
+    if (per_sm < 1) return set_error(CVCS_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %d B)", smem_bytes);
+    long long g = static_cast<long long>(per_sm) * num_sms();
+    if (g > kMaxGrid) g = kMaxGrid;
+    if (g > blocks_needed) g = blocks_needed;
+    if (g < 1) g = 1;
+    *grid_out = static_cast<int>(g);
+    return CVCS_OK;
+}
+
+// Classify a label: [0,C) -> itself, ignore_index outside [0,C) -> C, anything else -> C+1.
+__device__ __forceinline__ int hist_bin_u8(int t, int C, int ign_outside) {
+    return t < C ? t : (t == ign_outside ? C : C + 1);
+}
+__device__ __forceinline__ int hist_bin_i64(long long t, int C, long long ignore_index) {
+    return (t >= 0 && t < C) ? static_cast<int>(t) : (t == ignore_index ? C : C + 1);
+}
+
+// ---- K4 ------------------------------------------------------------------------------------
+struct HistParams {
+    const void* target;
+    long long n;            // pixels
+    unsigned long long* hist;  // nullable, accumulated into
+    const float* weight;    // nullable
+    double* tw_out;         // nullable {Σw, 1/Σw}
+    Workspace* ws;
+    long long ignore_index;
+    int C;
+    int target_i64;
+};
+
+template <bool PRIV>
+__global__ void __launch_bounds__(kThreads) label_hist_kernel(const HistParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned int is_last;
+    const int C = p.C;
+    const int nb = C + 2;
+    BinAcc<PRIV> acc;
+    acc.init(smem, nb);
+    unsigned int since_flush = 0;
+
+    if (!p.target_i64) {
+        const uint8_t* __restrict__ tgt = reinterpret_cast<const uint8_t*>(p.target);
+        const int ign_outside = (p.ignore_index >= C && p.ignore_index <= 255) ? static_cast<int>(p.ignore_index) : -1;
+        const long long n16 = p.n / 16;  // pointer is 16-byte aligned (checked on the host)
+        for (long long base = static_cast<long long>(blockIdx.x) * kThreads; base < n16;
+             base += static_cast<long long>(gridDim.x) * kThreads) {
+            const long long i = base + threadIdx.x;
+            if (i < n16) {
+                Raw<16> r;
+                r.load(tgt + 16 * i);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int t = (r.word(k / 4) >> (8 * (k % 4))) & 0xff;
+                    acc.add(hist_bin_u8(t, C, ign_outside));
+                }
+            }
+            if (PRIV) {
+                since_flush += 16;
+                if (since_flush > 65535u - 16u) {
+                    acc.flush(p.ws->hist);
+                    since_flush = 0;
+                }
+            }
+        }
+        // tail (< 16 pixels)
+        if (blockIdx.x == 0) {
+            const long long i = n16 * 16 + threadIdx.x;
+            if (i < p.n) acc.add(hist_bin_u8(tgt[i], C, ign_outside));
+        }
+    } else {
+        const long long* __restrict__ tgt = reinterpret_cast<const long long*>(p.target);
+        const long long n2 = p.n / 2;
+        for (long long base = static_cast<long long>(blockIdx.x) * kThreads; base < n2;
+             base += static_cast<long long>(gridDim.x) * kThreads) {
+            const long long i = base + threadIdx.x;
+            if (i < n2) {
+                Raw<16> r;
+                r.load(tgt + 2 * i);
+                const long long a = (static_cast<long long>(r.v.y) << 32) | r.v.x;
+                const long long b = (static_cast<long long>(r.v.w) << 32) | r.v.z;
+                acc.add(hist_bin_i64(a, C, p.ignore_index));
+                acc.add(hist_bin_i64(b, C, p.ignore_index));
+            }
+            if (PRIV) {
+                since_flush += 2;
+                if (since_flush > 65535u - 2u) {
+                    acc.flush(p.ws->hist);
+                    since_flush = 0;
+                }
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (p.n & 1)) acc.add(hist_bin_i64(tgt[p.n - 1], C, p.ignore_index));
+    }
+    acc.flush(p.ws->hist);
+
+    // last CTA: publish this call's histogram, Σw, and zero the scratch bins
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    __shared__ double tw_red[kWarps];
+    double tw = 0.0;
+    for (int b = threadIdx.x; b < nb; b += kThreads) {
+        const unsigned long long cnt = __ldcg(&p.ws->hist[b]);
+        p.ws->hist[b] = 0ull;
+        if (p.hist && cnt) atomicAdd(p.hist + b, cnt);
+        if (b < C && static_cast<long long>(b) != p.ignore_index)
+            tw += static_cast<double>(cnt) * static_cast<double>(p.weight ? p.weight[b] : 1.0f);
+    }
+    tw = warp_sum(tw);
+    if ((threadIdx.x & 31) == 0) tw_red[threadIdx.x >> 5] = tw;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += tw_red[w];
+        if (p.tw_out) {
+            p.tw_out[0] = s;
+            p.tw_out[1] = 1.0 / s;
+        }
+        p.ws->ticket = 0u;
+        __threadfence();
+    }
+}
+
+__global__ void total_weight_kernel(const unsigned long long* __restrict__ hist, const float* __restrict__ weight,
+                                    int C, long long ignore_index, double* __restrict__ out) {
+    // one warp; fixed order -> deterministic
+    double s = 0.0;
+    for (int c = threadIdx.x; c < C; c += 32)
+        if (static_cast<long long>(c) != ignore_index)
+            s += static_cast<double>(hist[c]) * static_cast<double>(weight ? weight[c] : 1.0f);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) {
+        out[0] = s;
+        out[1] = 1.0 / s;
+    }
+}
+
+// ---- grad scaling ------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) scale_kernel(T* __restrict__ x, long long n, const float* __restrict__ scale) {
+    constexpr int VEC = 16 / sizeof(T);
+    const float s = *scale;
+    const long long nv = n / VEC;
+    for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < nv;
+         i += static_cast<long long>(gridDim.x) * kThreads) {
+        float v[VEC];
+        VecIO<T, VEC>::load(x + i * VEC, v);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] *= s;
+        VecIO<T, VEC>::store(x + i * VEC, v);
+    }
+    if (blockIdx.x == 0) {
+        const long long i = nv * VEC + threadIdx.x;
+        if (i < n) {
+            float v[1];
+            VecIO<T, 1>::load(x + i, v);
+            v[0] *= s;
+            VecIO<T, 1>::store(x + i, v);
+        }
+    }
+}
+
+// ---- K2 ------------------------------------------------------------------------------------
+struct ArgmaxParams {
+    const void* logits;
+    void* out;
+    long long hw;
+    long long n_items;
+    unsigned int items_per_image;
+    int C;
+    int out_i64;
+};
+
+template <int VEC>
+__device__ __forceinline__ void store_index(void* outp, int out_i64, long long pix, const int (&a)[VEC]) {
+    if (out_i64) {
+        long long* out = reinterpret_cast<long long*>(outp) + pix;
+        if constexpr (VEC % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < VEC / 2; ++i) {
+                Raw<16> r;
+                r.v = make_uint4(static_cast<uint32_t>(a[2 * i]), 0u, static_cast<uint32_t>(a[2 * i + 1]), 0u);
+                r.store(out + 2 * i);
+            }
+        } else {
+            Raw<8> r;
+            r.v = make_uint2(static_cast<uint32_t>(a[0]), 0u);
+            r.store(out);
+        }
+    } else {
+        uint8_t* out = reinterpret_cast<uint8_t*>(outp) + pix;
+        if constexpr (VEC == 1) {
+            Raw<1> r;
+            r.v = static_cast<uint8_t>(a[0]);
+            r.store(out);
+        } else {
+            Raw<VEC> r;
+#pragma unroll
+            for (int i = 0; i < VEC / 4; ++i)
+                r.word(i) = static_cast<uint32_t>(a[4 * i]) | (static_cast<uint32_t>(a[4 * i + 1]) << 8) |
+                            (static_cast<uint32_t>(a[4 * i + 2]) << 16) | (static_cast<uint32_t>(a[4 * i + 3]) << 24);
+            r.store(out);
+        }
+    }
+}
+
+// NCHW: a thread owns VEC consecutive pixels and walks the class planes (4 planes in flight).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) argmax_nchw_kernel(const ArgmaxParams p) {
+    const T* __restrict__ logits = reinterpret_cast<const T*>(p.logits);
+    const int C = p.C;
+    for (long long base = static_cast<long long>(blockIdx.x) * kThreads; base < p.n_items;
+         base += static_cast<long long>(gridDim.x) * kThreads) {
+        const long long item = base + threadIdx.x;
+        if (item >= p.n_items) continue;
+        const unsigned int item32 = static_cast<unsigned int>(item);
+        const unsigned int b = item32 / p.items_per_image;
+        const unsigned int g = item32 - b * p.items_per_image;
+        const long long pix = static_cast<long long>(b) * p.hw + static_cast<long long>(g) * VEC;
+        const T* src = logits + static_cast<long long>(b) * C * p.hw + static_cast<long long>(g) * VEC;
+        float best[VEC];
+        int arg[VEC];
+        VecIO<T, VEC>::load(src, best);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) arg[v] = 0;
+        int c = 1;
+        for (; c + 4 <= C; c += 4) {
+            float x[4][VEC];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) VecIO<T, VEC>::load(src + (c + j) * p.hw, x[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (better(x[j][v], best[v])) {
+                        best[v] = x[j][v];
+                        arg[v] = c + j;
+                    }
+        }
+        for (; c < C; ++c) {
+            float x[VEC];
+            VecIO<T, VEC>::load(src + c * p.hw, x);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (better(x[v], best[v])) {
+                    best[v] = x[v];
+                    arg[v] = c;
+                }
+        }
+        store_index<VEC>(p.out, p.out_i64, pix, arg);
+    }
+}
+
+// Any layout via strides, one pixel per thread.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) argmax_generic_kernel(const ArgmaxParams p, long long class_stride,
+                                                                  long long pixel_stride, long long image_stride) {
+    const T* __restrict__ logits = reinterpret_cast<const T*>(p.logits);
+    const int C = p.C;
+    for (long long pix = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; pix < p.n_items;
+         pix += static_cast<long long>(gridDim.x) * kThreads) {
+        const long long b = pix / p.hw;
+        const T* src = logits + b * image_stride + (pix - b * p.hw) * pixel_stride;
+        float best[1];
+        VecIO<T, 1>::load(src, best);
+        int arg[1] = {0};
+        for (int c = 1; c < C; ++c) {
+            float x[1];
+            VecIO<T, 1>::load(src + c * class_stride, x);
+            if (better(x[0], best[0])) {
+                best[0] = x[0];
+                arg[0] = c;
+            }
+        }
+        store_index<1>(p.out, p.out_i64, pix, arg);
+    }
+}
+
+// ---- K3 ------------------------------------------------------------------------------------
+struct ConfParams {
+    const void* pred;
+    const void* target;
+    long long n;
+    unsigned long long* confmat;
+    unsigned long long* status;
+    long long ignore_index;
+    int C;
+    int pred_i64;
+    int target_i64;
+};
+
+template <int VEC>
+__device__ __forceinline__ void load_index(const void* base, int is_i64, long long i, long long (&v)[VEC]) {
+    if (is_i64) {
+        const long long* q = reinterpret_cast<const long long*>(base) + i;
+        if constexpr (VEC % 2 == 0) {
+#pragma unroll
+            for (int k = 0; k < VEC / 2; ++k) {
+                Raw<16> r;
+                r.load(q + 2 * k);
+                v[2 * k] = (static_cast<long long>(r.v.y) << 32) | r.v.x;
+                v[2 * k + 1] = (static_cast<long long>(r.v.w) << 32) | r.v.z;
+            }
+        } else {
+            v[0] = q[0];
+        }
+    } else {
+        const uint8_t* q = reinterpret_cast<const uint8_t*>(base) + i;
+        if constexpr (VEC == 1) {
+            v[0] = q[0];
+        } else {
+            Raw<VEC> r;
+            r.load(q);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) v[k] = (r.word(k / 4) >> (8 * (k % 4))) & 0xff;
+        }
+    }
+}
+
+template <bool PRIV, int VEC>
+__global__ void __launch_bounds__(kThreads) confmat_kernel(const ConfParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int C = p.C;
+    BinAcc<PRIV> acc;
+    acc.init(smem, C * C);
+    unsigned int since_flush = 0, bad = 0;
+    const long long nv = p.n / VEC;
+    auto one = [&](long long t, long long q) {
+        if (t == p.ignore_index) return;
+        if (t < 0 || t >= C || q < 0 || q >= C) {
+            ++bad;
+            return;
+        }
+        acc.add(static_cast<int>(t) * C + static_cast<int>(q));
+    };
+    for (long long base = static_cast<long long>(blockIdx.x) * kThreads; base < nv;
+         base += static_cast<long long>(gridDim.x) * kThreads) {
+        const long long i = base + threadIdx.x;
+        if (i < nv) {
+            long long t[VEC], q[VEC];
+            load_index<VEC>(p.target, p.target_i64, i * VEC, t);
+            load_index<VEC>(p.pred, p.pred_i64, i * VEC, q);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) one(t[k], q[k]);
+        }
+        if (PRIV) {
+            since_flush += VEC;
+            if (since_flush > 65535u - VEC) {
+                acc.flush(p.confmat);
+                since_flush = 0;
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        const long long i = nv * VEC + threadIdx.x;
+        if (i < p.n) {
+            long long t[1], q[1];
+            load_index<1>(p.target, p.target_i64, i, t);
+            load_index<1>(p.pred, p.pred_i64, i, q);
+            one(t[0], q[0]);
+        }
+    }
+    acc.flush(p.confmat);
+    bad = warp_sum(bad);
+    if ((threadIdx.x & 31) == 0 && bad && p.status) atomicAdd(p.status, static_cast<unsigned long long>(bad));
+}
+
+bool aligned_to(const void* q, size_t a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; }
+
+}  // namespace
+
+int label_hist_launch(const void* target, int target_dtype, long long n, int C, long long ignore_index,
+                      unsigned long long* hist, const float* weight, double* tw_out, void* workspace,
+                      cudaStream_t stream) {
+    CVCS_REQUIRE((target || n == 0) && workspace, "cvcs_label_hist: NULL target/workspace");
+    CVCS_REQUIRE(target_dtype == CVCS_U8 || target_dtype == CVCS_I64, "cvcs_label_hist: target dtype tag %d (want u8/i64)", target_dtype);
+    CVCS_REQUIRE(n >= 0 && C >= 1, "cvcs_label_hist: bad n=%lld C=%d", n, C);
+    if (C + 2 > kMaxHistBins) return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_label_hist: C=%d > %d", C, kMaxHistBins - 2);
+    CVCS_REQUIRE(aligned_to(target, 16), "cvcs_label_hist: target must be 16-byte aligned");
+    HistParams p{};
+    p.target = target;
+    p.n = n;
+    p.hist = hist;
+    p.weight = weight;
+    p.tw_out = tw_out;
+    p.ws = reinterpret_cast<Workspace*>(workspace);
+    p.ignore_index = ignore_index;
+    p.C = C;
+    p.target_i64 = target_dtype == CVCS_I64;
+    const int per = p.target_i64 ? 2 : 16;
+    const long long blocks = (n / per + kThreads - 1) / kThreads;
+    int grid = 0;
+    if (C + 2 <= 64) {
+        const int smem = BinAcc<true>::smem_bytes(C + 2);
+        int rc = grid_for(label_hist_kernel<true>, smem, blocks, &grid);
+        if (rc) return rc;
+        label_hist_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+    } else {
+        const int smem = BinAcc<false>::smem_bytes(C + 2);
+        int rc = grid_for(label_hist_kernel<false>, smem, blocks, &grid);
+        if (rc) return rc;
+        label_hist_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+    }
+    CVCS_CUDA_OK(cudaGetLastError());
+    return CVCS_OK;
+}
+
+int total_weight_launch(const unsigned long long* hist, const float* weight, int C, long long ignore_index,
+                        double* out, cudaStream_t stream) {
+    CVCS_REQUIRE(hist && out && C >= 1, "cvcs_total_weight: NULL hist/out or C < 1");
+    total_weight_kernel<<<1, 32, 0, stream>>>(hist, weight, C, ignore_index, out);
+    CVCS_CUDA_OK(cudaGetLastError());
+    return CVCS_OK;
+}
+
+int scale_launch(void* x, int dtype, long long n, const float* scale, cudaStream_t stream) {
+    CVCS_REQUIRE(x && scale && n >= 0, "cvcs_scale_inplace: NULL x/scale");
+    CVCS_REQUIRE(dtype == CVCS_F32 || dtype == CVCS_BF16, "cvcs_scale_inplace: dtype tag %d", dtype);
+    CVCS_REQUIRE(aligned_to(x, 16), "cvcs_scale_inplace: x must be 16-byte aligned");
+    const long long per = dtype == CVCS_F32 ? 4 : 8;
+    long long blocks = (n / per + kThreads - 1) / kThreads;
+    long long g = static_cast<long long>(num_sms()) * 8;
+    if (g > blocks) g = blocks;
+    if (g < 1) g = 1;
+    if (dtype == CVCS_F32) scale_kernel<float><<<static_cast<int>(g), kThreads, 0, stream>>>(reinterpret_cast<float*>(x), n, scale);
+    else scale_kernel<__nv_bfloat16><<<static_cast<int>(g), kThreads, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(x), n, scale);
+    CVCS_CUDA_OK(cudaGetLastError());
+    return CVCS_OK;
+}
+
+int argmax_launch(const void* logits, int logits_dtype, int layout, int B, int C, int H, int W, void* out,
+                  int out_dtype, cudaStream_t stream) {
+    CVCS_REQUIRE(logits && out, "cvcs_argmax: NULL logits/out");
+    CVCS_REQUIRE(logits_dtype == CVCS_F32 || logits_dtype == CVCS_BF16, "cvcs_argmax: logits dtype tag %d", logits_dtype);
+    CVCS_REQUIRE(layout == CVCS_NCHW || layout == CVCS_NHWC, "cvcs_argmax: layout %d", layout);
+    CVCS_REQUIRE(out_dtype == CVCS_U8 || out_dtype == CVCS_I64, "cvcs_argmax: out dtype tag %d", out_dtype);
+    CVCS_REQUIRE(B > 0 && C >= 1 && H > 0 && W > 0, "cvcs_argmax: bad shape");
+    CVCS_REQUIRE(!(out_dtype == CVCS_U8 && C > 256), "cvcs_argmax: u8 output needs C <= 256");
+    const long long hw = static_cast<long long>(H) * W, n = hw * B;
+    CVCS_REQUIRE(n < (1ll << 33), "cvcs_argmax: too many pixels");
+    ArgmaxParams p{};
+    p.logits = logits;
+    p.out = out;
+    p.hw = hw;
+    p.C = C;
+    p.out_i64 = out_dtype == CVCS_I64;
+    const int esize = logits_dtype == CVCS_F32 ? 4 : 2;
+    const int vec = logits_dtype == CVCS_F32 ? 4 : 8;
+    const bool fast = layout == CVCS_NCHW && hw % vec == 0 && aligned_to(logits, static_cast<size_t>(vec) * esize) &&
+                      aligned_to(out, p.out_i64 ? 16 : vec);
+    int grid = 0;
+    if (fast) {
+        p.n_items = n / vec;
+        p.items_per_image = static_cast<unsigned int>(hw / vec);
+        const long long blocks = (p.n_items + kThreads - 1) / kThreads;
+        if (logits_dtype == CVCS_F32) {
+            int rc = grid_for(argmax_nchw_kernel<float, 4>, 0, blocks, &grid);
+            if (rc) return rc;
+            argmax_nchw_kernel<float, 4><<<grid, kThreads, 0, stream>>>(p);
+        } else {
+            int rc = grid_for(argmax_nchw_kernel<__nv_bfloat16, 8>, 0, blocks, &grid);
+            if (rc) return rc;
+            argmax_nchw_kernel<__nv_bfloat16, 8><<<grid, kThreads, 0, stream>>>(p);
+        }
+    } else {
+        p.n_items = n;
+        const long long cs = layout == CVCS_NCHW ? hw : 1, ps = layout == CVCS_NCHW ? 1 : C;
+        const long long is = static_cast<long long>(C) * hw;
+        const long long blocks = (n + kThreads - 1) / kThreads;
+        if (logits_dtype == CVCS_F32) {
+            int rc = grid_for(argmax_generic_kernel<float>, 0, blocks, &grid);
+            if (rc) return rc;
+            argmax_generic_kernel<float><<<grid, kThreads, 0, stream>>>(p, cs, ps, is);
+        } else {
+            int rc = grid_for(argmax_generic_kernel<__nv_bfloat16>, 0, blocks, &grid);
+            if (rc) return rc;
+            argmax_generic_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(p, cs, ps, is);
+        }
+    }
+    CVCS_CUDA_OK(cudaGetLastError());
+    return CVCS_OK;
+}
+
+int confmat_launch(const void* pred, int pred_dtype, const void* target, int target_dtype, long long n, int C,
+                   long long ignore_index, unsigned long long* confmat, unsigned long long* status, void* workspace,
+                   cudaStream_t stream) {
+    (void)workspace;
+    CVCS_REQUIRE(((pred && target) || n == 0) && confmat, "cvcs_confmat: NULL pred/target/confmat");
+    CVCS_REQUIRE(pred_dtype == CVCS_U8 || pred_dtype == CVCS_I64, "cvcs_confmat: pred dtype tag %d (want u8/i64)", pred_dtype);
+    CVCS_REQUIRE(target_dtype == CVCS_U8 || target_dtype == CVCS_I64, "cvcs_confmat: target dtype tag %d (want u8/i64)", target_dtype);
+    CVCS_REQUIRE(n >= 0 && C >= 1, "cvcs_confmat: bad n/C");
+    if (C > 200) return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_confmat: C=%d > 200 (bins do not fit shared memory)", C);
+    ConfParams p{};
+    p.pred = pred;
+    p.target = target;
+    p.n = n;
+    p.confmat = confmat;
+    p.status = status;
+    p.ignore_index = ignore_index;
+    p.C = C;
+    p.pred_i64 = pred_dtype == CVCS_I64;
+    p.target_i64 = target_dtype == CVCS_I64;
+    const bool vec_ok = aligned_to(pred, 16) && aligned_to(target, 16);
+    const bool priv = C * C <= 64;
+    int grid = 0;
+    int rc;
+#define CVCS_LAUNCH_CONF(PRIV, VEC)                                                     \
+    do {                                                                                \
+        const int smem = BinAcc<PRIV>::smem_bytes(C * C);                               \
+        const long long blocks = (n / VEC + kThreads - 1) / kThreads;                   \
+        rc = grid_for(confmat_kernel<PRIV, VEC>, smem, blocks, &grid);                  \
+        if (rc) return rc;                                                              \
+        confmat_kernel<PRIV, VEC><<<grid, kThreads, smem, stream>>>(p);                 \
+    } while (0)
+    // 4 pixels per thread when both maps are u8 (32-bit loads) or any i64 (2 x 128-bit loads)
+    if (vec_ok) {
+        if (priv) CVCS_LAUNCH_CONF(true, 4);
+        else CVCS_LAUNCH_CONF(false, 4);
+    } else {
+        if (priv) CVCS_LAUNCH_CONF(true, 1);
+        else CVCS_LAUNCH_CONF(false, 1);
+    }
+#undef CVCS_LAUNCH_CONF
+    CVCS_CUDA_OK(cudaGetLastError());
+    return CVCS_OK;
+}
+
+}  // namespace cvcs

@@ -1,0 +1,200 @@
+"""Drop-in for the reference's loss boundary.
+
+Reference: ``utils.load_loss`` (utils.py:223-242) returns ``nn.CrossEntropyLoss(weight,
+ignore_index)``; the training loop calls ``loss = crit(mask_pred, mask.type(torch.long))``
+followed by ``loss.item()`` and ``loss.backward()`` (train.py:122-125); validation calls the
+same criterion under ``torch.no_grad()`` (utils.py:120).
+
+``FusedCrossEntropyLoss`` keeps that call signature.  One CUDA pass (K1) produces the loss AND
+the logit gradients (and, on request, the argmax map and the confusion-matrix update);
+``backward`` only hands the stashed gradient to autograd.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+# GID-15 class names, as printed by the reference's weight table (utils.py:23-40)
+GID15_LABELS = {
+    0: "unlabeled", 1: "industrial land", 2: "urban residential", 3: "rural residential", 4: "traffic land",
+    5: "paddy field", 6: "irrigated cropland", 7: "dry cropland", 8: "garden plot", 9: "arbor forest",
+    10: "shrub land", 11: "natural grassland", 12: "artificial grassland", 13: "river", 14: "lake", 15: "pond",
+}
+
+
+def _as_bchw(logits: torch.Tensor, target: torch.Tensor):
+    """Normalise nn.CrossEntropyLoss input conventions to [B,C,H,W] / [B,H,W] views.
+    Returns (logits4, target3, restore) where restore maps a gradient laid out like logits4
+    back to the caller's input shape."""
+    shape = logits.shape
+    if logits.dim() == 4:
+        return logits, target, (lambda d: d)
+    if logits.dim() == 2:  # [N, C] with target [N]: N pixels, classes innermost (an NHWC image)
+        n, c = shape
+        x = logits.contiguous().view(1, n, 1, c).permute(0, 3, 1, 2)
+        return x, target.reshape(1, n, 1), (lambda d: d.permute(0, 2, 3, 1).reshape(n, c))
+    if logits.dim() == 3:  # [B, C, L]
+        b, c, l = shape
+        return logits.reshape(b, c, l, 1), target.reshape(b, l, 1), (lambda d: d.reshape(shape))
+    if logits.dim() > 4:   # [B, C, d1, d2, ...]
+        b, c = shape[:2]
+        return logits.reshape(b, c, -1, 1), target.reshape(b, -1, 1), (lambda d: d.reshape(shape))
+    raise RuntimeError(f"FusedCrossEntropyLoss: unsupported input shape {tuple(shape)}")
+
+
+class _FusedCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, module):
+        want_grad = torch.is_grad_enabled() and logits.requires_grad
+        loss, dlogits, restore = module._run(logits, target, want_grad)
+        ctx.module = module
+        ctx.restore = restore
+        ctx.dlogits = dlogits
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        d = ctx.dlogits
+        if d is None:
+            raise RuntimeError("FusedCrossEntropyLoss: backward called but the forward ran without grad")
+        ctx.dlogits = None
+        mode = ctx.module.grad_scale_mode
+        if mode == "check":
+            # `loss.backward()` feeds exactly 1.0 (train.py:125); the reference loop has already
+            # synchronised on loss.item(), so reading 4 bytes here costs no extra bubble.
+            if float(grad_output) != 1.0:
+                ops.scale_inplace(d, grad_output.to(torch.float32).reshape(1))
+        elif mode == "scale":
+            ops.scale_inplace(d, grad_output.to(torch.float32).reshape(1))
+        # mode == "unit": trust the caller that grad_output == 1
+        return ctx.restore(d), None, None
+
+
+class FusedCrossEntropyLoss(nn.Module):
+    """``nn.CrossEntropyLoss(weight=..., ignore_index=..., reduction='mean')`` on the fused kernel.
+
+    Extras over the reference signature (all optional):
+      confusion      a ``cvcs_b200.metrics.MulticlassConfusionMatrix`` to update in the same pass
+      return_argmax  keep the argmax map of the last call in ``self.last_argmax`` (uint8)
+      grad_scale_mode  'check' (default) | 'unit' | 'scale' — how ``grad_output`` is honoured
+      strict         synchronise after every call and raise IndexError on out-of-bounds labels
+                     (default: the loss is NaN-poisoned and ``check_errors()`` raises)
+    Targets may be int64 (as the reference passes) or uint8 (as the masks are stored: skips the
+    8x wider label read).
+    """
+
+    def __init__(self, weight: Optional[torch.Tensor] = None, ignore_index: int = -100, reduction: str = "mean",
+                 label_smoothing: float = 0.0, confusion=None, return_argmax: bool = False,
+                 grad_scale_mode: str = "check", strict: bool = False):
+        super().__init__()
+        if reduction != "mean" or label_smoothing != 0.0:
+            raise NotImplementedError("the reference only uses reduction='mean', label_smoothing=0 (utils.py:230,238)")
+        if grad_scale_mode not in ("check", "unit", "scale"):
+            raise ValueError("grad_scale_mode must be 'check', 'unit' or 'scale'")
+        self.register_buffer("weight", None if weight is None else weight.detach().clone())
+        self.ignore_index = int(ignore_index)
+        self.confusion = confusion
+        self.return_argmax = return_argmax
+        self.grad_scale_mode = grad_scale_mode
+        self.strict = strict
+        self.last_argmax: Optional[torch.Tensor] = None
+        self.last_sums: Optional[torch.Tensor] = None  # f64[3] {Σ w·nll, Σ w, #out-of-bounds}
+        self._w32: Optional[torch.Tensor] = None
+
+    # -- helpers -------------------------------------------------------------------------------------
+    def _weight_f32(self, dev: torch.device) -> Optional[torch.Tensor]:
+        if self.weight is None:
+            return None
+        if self._w32 is None or self._w32.device != dev:
+            self._w32 = self.weight.to(device=dev, dtype=torch.float32).contiguous()
+        return self._w32
+
+    def _run(self, logits: torch.Tensor, target: torch.Tensor, want_grad: bool):
+        if not logits.is_cuda:
+            raise RuntimeError("FusedCrossEntropyLoss needs CUDA tensors (cvcs_b200 has no CPU fallback)")
+        if logits.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError(f"FusedCrossEntropyLoss: logits must be float32 or bfloat16, got {logits.dtype}")
+        if target.dtype not in (torch.int64, torch.uint8):
+            # same complaint torch makes
+            raise RuntimeError(f"expected scalar type Long but found {str(target.dtype).replace('torch.', '')}")
+        x, t, restore = _as_bchw(logits, target)
+        B, C, H, W = x.shape
+        dev = x.device
+        w = self._weight_f32(dev)
+        if w is not None and w.numel() != C:
+            raise RuntimeError(f"weight tensor should be defined either for all {C} classes or no classes "
+                               f"but got weight tensor of shape: {list(w.shape)}")
+        inv_tw, inv_tw_dev = 0.0, None
+        if want_grad:
+            if w is None and t.dtype == torch.uint8 and not (0 <= self.ignore_index <= 255):
+                inv_tw = 1.0 / float(B * H * W)  # nothing can be ignored: Σ v·w is the pixel count
+            else:
+                tw = torch.empty(2, dtype=torch.float64, device=dev)
+                ops.label_hist(t, C, self.ignore_index, hist=None, weight=w, total_weight_out=tw)
+                inv_tw_dev = tw[1:]
+        argmax = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if (self.return_argmax and C <= 256) else None
+        conf = None
+        if self.confusion is not None:
+            conf = self.confusion._state_for(dev, C)
+        loss_out, sums, dlogits = ops.ce_fused(x, t, w, self.ignore_index, want_grad=want_grad,
+                                               inv_total_weight=inv_tw, inv_total_weight_dev=inv_tw_dev,
+                                               argmax=argmax, confmat=conf)
+        self.last_argmax = argmax
+        self.last_sums = sums
+        if self.strict:
+            self.check_errors()
+        loss = loss_out.reshape(())
+        if logits.dtype != torch.float32:
+            loss = loss.to(logits.dtype)  # torch returns the loss in the logits dtype
+        return loss, dlogits, restore
+
+    def check_errors(self) -> None:
+        """Raise what torch raises on an out-of-bounds label (synchronises)."""
+        if self.last_sums is not None and float(self.last_sums[2]) > 0:
+            raise IndexError("Target is out of bounds.")
+
+    def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return _FusedCE.apply(input, target, self)
+
+
+def class_weights_from_counts(counts: torch.Tensor, ignore_background: bool = False) -> torch.Tensor:
+    """Reference weighting rule ``w_c = Σn / (bins · n_c)``, 0 for empty classes, background
+    forced to 0 when ignored (dataset.py:360-384), evaluated exactly as the reference does:
+    float32 counts, Python-float division of a float32 tensor numerator."""
+    counts = counts.detach().to("cpu", torch.float32)
+    if ignore_background:
+        counts = counts[1:]
+    numerator = torch.sum(counts)
+    bins = len(counts)
+    w = []
+    for cc in counts:
+        n = cc.item()
+        w.append(0 if n == 0 else numerator / (bins * n))
+    wt = torch.tensor(w)
+    if ignore_background:
+        return torch.concat((torch.tensor([0]), wt), dim=0)
+    return wt
+
+
+def load_loss(config: dict, device, dataset=None):
+    """Same signature and config keys as the reference's ``utils.load_loss`` (utils.py:223-242):
+    ``loss`` in {CEL, wCEL, MSE}, ``num_classes`` (+1 for background), ``ignore_background``."""
+    classes = config["num_classes"] + 1
+    name = config["loss"]
+    ignore_background = config.get("ignore_background", False)
+    ignore_index = 0 if ignore_background else -100
+    if name == "CEL":
+        return FusedCrossEntropyLoss(ignore_index=ignore_index).to(device)
+    if name == "wCEL":
+        print("Computing class weights, it might take several minutes...", flush=True)
+        weights = dataset.get_class_weights(classes, ignore_background).to(device)
+        for i, score in enumerate(weights):
+            print(f"{GID15_LABELS.get(i, i)!s:>22}  {score.item():.6f}", flush=True)
+        return FusedCrossEntropyLoss(weight=weights, ignore_index=ignore_index).to(device)
+    if name == "MSE":
+        return nn.MSELoss()  # not on the hot path (no shipped net regresses); kept for config parity
+    raise Exception

@@ -1,0 +1,277 @@
+"""Functional wrappers: torch CUDA tensors -> raw pointers -> the C-ABI kernels.
+
+PyTorch is only plumbing here (device memory, streams); every computation below happens in
+libcvcs_b200.so.  CPU tensors are rejected: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+_DTYPE_TAG = {
+    torch.float32: _lib.F32,
+    torch.bfloat16: _lib.BF16,
+    torch.uint8: _lib.U8,
+    torch.int64: _lib.I64,
+    torch.int32: _lib.I32,
+}
+
+_workspaces: dict = {}
+
+
+def _tag(t: torch.Tensor) -> int:
+    try:
+        return _DTYPE_TAG[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"cvcs_b200: unsupported dtype {t.dtype}") from None
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("cvcs_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"cvcs_b200: tensors on different devices ({dev} vs {t.device})")
+    assert dev is not None
+    return dev
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def workspace(dev: torch.device) -> torch.Tensor:
+    """Zero-initialised scratch buffer, one per (device, stream); kernels leave it zeroed."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev))
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.workspace_bytes(), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
+def logits_layout(logits: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """[B,C,H,W] logits -> (tensor whose memory the kernel may read as-is, layout tag)."""
+    if logits.is_contiguous():
+        return logits, _lib.NCHW
+    if logits.dim() == 4 and logits.is_contiguous(memory_format=torch.channels_last):
+        return logits, _lib.NHWC
+    return logits.contiguous(), _lib.NCHW
+
+
+# ---- K4 ------------------------------------------------------------------------------------------
+def label_hist(target: torch.Tensor, num_classes: int, ignore_index: int = -100,
+               hist: Optional[torch.Tensor] = None, weight: Optional[torch.Tensor] = None,
+               total_weight_out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Accumulate the label histogram (int64[C+2]: classes, ignored-outside, out-of-bounds)."""
+    dev = _need_cuda(target, hist, weight, total_weight_out)
+    target = target.contiguous()
+    if target.dtype not in (torch.uint8, torch.int64):
+        raise RuntimeError(f"expected scalar type Long or Byte but found {target.dtype}")
+    if hist is None and total_weight_out is None:
+        hist = torch.zeros(num_classes + 2, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_label_hist(target.data_ptr(), _tag(target), target.numel(), num_classes, ignore_index,
+                                  _ptr(hist), _ptr(weight), _ptr(total_weight_out), workspace(dev).data_ptr(),
+                                  _stream(dev)))
+    return hist
+
+
+def total_weight(hist: torch.Tensor, weight: Optional[torch.Tensor], num_classes: int, ignore_index: int,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _need_cuda(hist, weight, out)
+    if out is None:
+        out = torch.empty(2, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_total_weight(hist.data_ptr(), _ptr(weight), num_classes, ignore_index, out.data_ptr(),
+                                    _stream(dev)))
+    return out
+
+
+# ---- K1 ------------------------------------------------------------------------------------------
+def ce_fused(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor] = None,
+             ignore_index: int = -100, *, want_grad: bool = True, inv_total_weight: float = 0.0,
+             inv_total_weight_dev: Optional[torch.Tensor] = None, dlogits: Optional[torch.Tensor] = None,
+             argmax: Optional[torch.Tensor] = None, confmat: Optional[torch.Tensor] = None,
+             loss_sums: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None):
+    """One fused pass. logits [B,C,H,W] f32/bf16 (contiguous or channels_last), target [B,H,W]
+    u8/i64.  Returns (loss_out f32[1], loss_sums f64[3], dlogits or None)."""
+    dev = _need_cuda(logits, target, weight, inv_total_weight_dev, dlogits, argmax, confmat, loss_sums, loss_out)
+    if logits.dim() != 4:
+        raise RuntimeError(f"cvcs_b200.ce_fused expects [B,C,H,W] logits, got {tuple(logits.shape)}")
+    B, Cc, H, W = logits.shape
+    if tuple(target.shape) != (B, H, W):
+        raise RuntimeError(f"size mismatch (got input: {list(logits.shape)} , target: {list(target.shape)}")
+    logits, layout = logits_layout(logits)
+    target = target.contiguous()
+    if want_grad and dlogits is None:
+        dlogits = torch.empty_like(logits)  # preserves the memory format
+    if loss_sums is None:
+        loss_sums = torch.empty(3, dtype=torch.float64, device=dev)
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_ce_fused(logits.data_ptr(), _tag(logits), layout, target.data_ptr(), _tag(target),
+                                _ptr(weight), ignore_index, B, Cc, H, W, float(inv_total_weight),
+                                _ptr(inv_total_weight_dev), _ptr(dlogits) if want_grad else None, _ptr(argmax),
+                                _tag(argmax) if argmax is not None else _lib.U8, _ptr(confmat),
+                                loss_sums.data_ptr(), loss_out.data_ptr(), workspace(dev).data_ptr(), _stream(dev)))
+    return loss_out, loss_sums, (dlogits if want_grad else None)
+
+
+def scale_inplace(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    dev = _need_cuda(x, scale)
+    assert scale.dtype == torch.float32 and scale.numel() == 1
+    with torch.cuda.device(dev):
+        check(lib.cvcs_scale_inplace(x.data_ptr(), _tag(x), x.numel(), scale.data_ptr(), _stream(dev)))
+    return x
+
+
+# ---- K2 / K3 ---------------------------------------------------------------------------------------
+def argmax(logits: torch.Tensor, out_dtype: torch.dtype = torch.int64) -> torch.Tensor:
+    """First-maximal class index over dim 1 of [B,C,H,W] logits (torch.max / argmax semantics)."""
+    dev = _need_cuda(logits)
+    if logits.dim() != 4:
+        raise RuntimeError(f"cvcs_b200.argmax expects [B,C,H,W], got {tuple(logits.shape)}")
+    logits, layout = logits_layout(logits)
+    B, Cc, H, W = logits.shape
+    out = torch.empty((B, H, W), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_argmax(logits.data_ptr(), _tag(logits), layout, B, Cc, H, W, out.data_ptr(), _tag(out),
+                              _stream(dev)))
+    return out
+
+
+def confmat_update(confmat: torch.Tensor, preds: torch.Tensor, target: torch.Tensor, num_classes: int,
+                   ignore_index: Optional[int], status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """confmat[t, p] += 1 over index maps (any shape, same numel); int64[C,C] accumulated."""
+    dev = _need_cuda(confmat, preds, target, status)
+    preds, target = preds.contiguous(), target.contiguous()
+    if preds.numel() != target.numel():
+        raise RuntimeError("preds and target must have the same number of elements")
+    ign = -(1 << 62) if ignore_index is None else int(ignore_index)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_confmat(preds.data_ptr(), _tag(preds), target.data_ptr(), _tag(target), target.numel(),
+                               num_classes, ign, confmat.data_ptr(), _ptr(status), workspace(dev).data_ptr(),
+                               _stream(dev)))
+    return confmat
+
+
+# ---- K5 ------------------------------------------------------------------------------------------
+def tile_normalize(scene: torch.Tensor, tile_yx: torch.Tensor, tile_hw: Tuple[int, int],
+                   mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None,
+                   out_dtype: torch.dtype = torch.float32, label: Optional[torch.Tensor] = None,
+                   label_out_dtype: torch.dtype = torch.uint8, hist: Optional[torch.Tensor] = None,
+                   hist_classes: int = 0, hist_ignore_index: int = -100):
+    """scene u8 [Cb,H,W] -> tiles [n,Cb,th,tw] (cast / normalised), label u8 [H,W] -> [n,th,tw]."""
+    dev = _need_cuda(scene, tile_yx, mean, std, label, hist)
+    assert scene.dtype == torch.uint8 and scene.dim() == 3 and scene.is_contiguous()
+    assert tile_yx.dtype == torch.int32 and tile_yx.dim() == 2 and tile_yx.shape[1] == 2 and tile_yx.is_contiguous()
+    Cb, H, W = scene.shape
+    th, tw = tile_hw
+    n = tile_yx.shape[0]
+    out = torch.empty((n, Cb, th, tw), dtype=out_dtype, device=dev)
+    label_out = None
+    if label is not None:
+        assert label.dtype == torch.uint8 and tuple(label.shape[-2:]) == (H, W) and label.is_contiguous()
+        label_out = torch.empty((n, th, tw), dtype=label_out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_tile_normalize(scene.data_ptr(), Cb, H, W, tile_yx.data_ptr(), n, th, tw, _ptr(mean), _ptr(std),
+                                      out.data_ptr(), _tag(out), _ptr(label), _ptr(label_out),
+                                      _tag(label_out) if label_out is not None else _lib.U8, _ptr(hist),
+                                      hist_classes, hist_ignore_index, workspace(dev).data_ptr(), _stream(dev)))
+    return out, label_out
+
+
+# ---- N2 / N3 / N4 ----------------------------------------------------------------------------------
+def vote(maps: torch.Tensor, num_classes: int = 0, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Per-pixel majority vote over dim 0 (ties -> smallest index, as torch.mode)."""
+    dev = _need_cuda(maps)
+    maps = maps.contiguous()
+    out = torch.empty(maps.shape[1:], dtype=out_dtype or maps.dtype, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_vote(maps.data_ptr(), _tag(maps), maps.shape[0], out.numel(), num_classes, out.data_ptr(),
+                            _tag(out), _stream(dev)))
+    return out
+
+
+def colorize(index_map: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
+    """[H,W] class indices -> [H,W,3] f32 colours (GID15Converter.iconvert)."""
+    dev = _need_cuda(index_map, lut)
+    index_map = index_map.contiguous()
+    lut = lut.contiguous().to(torch.float32)
+    out = torch.empty((*index_map.shape, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_colorize(index_map.data_ptr(), _tag(index_map), index_map.numel(), lut.data_ptr(),
+                                lut.shape[0], out.data_ptr(), _stream(dev)))
+    return out
+
+
+def stitch(tiles: torch.Tensor, tile_yx: torch.Tensor, scene_hw: Tuple[int, int],
+           crop_hw: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Paste u8 tiles [n,th,tw] (optionally their centred crop) into a scene-sized u8 map."""
+    dev = _need_cuda(tiles, tile_yx, out)
+    assert tiles.dtype == torch.uint8 and tiles.dim() == 3
+    tiles = tiles.contiguous()
+    n, th, tw = tiles.shape
+    ch, cw = crop_hw if crop_hw is not None else (th, tw)
+    H, W = scene_hw
+    if out is None:
+        out = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_stitch(tiles.data_ptr(), n, th, tw, tile_yx.data_ptr(), ch, cw, out.data_ptr(), H, W,
+                              _stream(dev)))
+    return out
+
+
+# ---- host-buffer context -------------------------------------------------------------------------
+class HostContext:
+    """cvcs_host_* : the C-ABI call a non-torch caller makes, on HOST buffers (copies inside)."""
+
+    def __init__(self, device: int, max_pixels: int, max_classes: int, logits_dtype: torch.dtype = torch.float32):
+        self._h = ctypes.c_void_p()
+        check(lib.cvcs_host_ctx_create(ctypes.byref(self._h), device, max_pixels, max_classes,
+                                       _DTYPE_TAG[logits_dtype]))
+        self.device = device
+
+    def close(self) -> None:
+        if self._h:
+            lib.cvcs_host_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ce_fused(self, logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor], ignore_index: int,
+                 want_grad: bool = True, dlogits: Optional[torch.Tensor] = None,
+                 argmax: Optional[torch.Tensor] = None, confmat: Optional[torch.Tensor] = None):
+        """All tensors are CPU tensors (ideally pinned).  Returns (loss float32 tensor[1], sums f64[3])."""
+        for t in (logits, target, weight, dlogits, argmax, confmat):
+            if t is not None and t.is_cuda:
+                raise RuntimeError("HostContext.ce_fused takes host tensors")
+        B, Cc, H, W = logits.shape
+        logits, layout = logits_layout(logits)
+        loss = torch.empty(1, dtype=torch.float32)
+        sums = torch.empty(3, dtype=torch.float64)
+        check(lib.cvcs_host_ce_fused(self._h, logits.data_ptr(), _tag(logits), layout, target.data_ptr(), _tag(target),
+                                     _ptr(weight), ignore_index, B, Cc, H, W, 1 if want_grad else 0, _ptr(dlogits),
+                                     _ptr(argmax), _tag(argmax) if argmax is not None else _lib.U8, _ptr(confmat),
+                                     loss.data_ptr(), sums.data_ptr()))
+        return loss, sums

@@ -1,0 +1,271 @@
+"""K1 parity (through the C-ABI): fused softmax-CE fwd+bwd + argmax + confusion matrix.
+
+Bars (BASELINE.json): argmax maps and confusion matrices bit-exact; loss and gradients within
+1e-5 relative for fp32 logits, 1e-2 for bf16 logits.  "Relative" for the gradient tensor is
+max|a-b| <= tol * max|b| (the gradients of one batch share one scale, 1/Σw).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, torch_path
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL, BF16_TOL = 1e-5, 1e-2
+PATHS = {"tma": 1, "direct": 2, "generic": 3, "auto": 0}
+
+
+@pytest.fixture()
+def lib():
+    from cvcs_b200 import _lib
+    yield _lib
+    _lib.set_option(_lib.OPT_CE_PATH, 0)
+    _lib.set_option(_lib.OPT_TMA_STAGES, 0)
+
+
+def run_k1(logits, target, weight, ignore_index, *, want_grad=True, layout="NCHW", label_dtype=torch.uint8,
+           argmax_dtype=torch.uint8, dtype=torch.float32, num_classes=None):
+    """Returns loss(float), sums(np f64[3]), grad(np f32, NCHW) | None, argmax(np i64), confmat(np i64)."""
+    from cvcs_b200 import ops
+    dev = torch.device("cuda", 0)
+    x = torch.as_tensor(logits).to(dev).to(dtype)
+    if layout == "NHWC":
+        x = x.contiguous(memory_format=torch.channels_last)
+    t = torch.as_tensor(target).to(dev).to(label_dtype)
+    B, C, H, W = x.shape
+    w = None if weight is None else torch.as_tensor(weight, dtype=torch.float32).to(dev)
+    inv_dev = None
+    if want_grad:
+        tw = torch.empty(2, dtype=torch.float64, device=dev)
+        ops.label_hist(t, C, ignore_index, weight=w, total_weight_out=tw)
+        inv_dev = tw[1:]
+    am = torch.full((B, H, W), 99, dtype=argmax_dtype, device=dev)
+    cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
+    loss, sums, d = ops.ce_fused(x, t, w, ignore_index, want_grad=want_grad, inv_total_weight_dev=inv_dev,
+                                 argmax=am, confmat=cm)
+    torch.cuda.synchronize()
+    if d is not None:
+        assert d.dtype == x.dtype and d.stride() == x.stride()
+        d = d.float().cpu().numpy()
+    return float(loss.item()), sums.cpu().numpy(), d, am.cpu().numpy().astype(np.int64), cm.cpu().numpy()
+
+
+def check_against(loss, grad, am, cm, logits, target, weight, ignore_index, tol):
+    C = logits.shape[1]
+    l_ref, sums_ref, g_ref = c_oracle.cross_entropy(logits, target, weight, ignore_index)
+    if np.isnan(l_ref):
+        assert np.isnan(loss)
+    else:
+        assert abs(loss - l_ref) <= tol * abs(l_ref), (loss, l_ref)
+    if grad is not None:
+        scale = max(np.abs(g_ref).max(), 1e-30)
+        assert np.abs(grad - g_ref).max() <= tol * scale, np.abs(grad - g_ref).max() / scale
+        ign = (target == ignore_index)
+        assert np.all(grad[np.broadcast_to(ign[:, None], grad.shape)] == 0)   # exact zeros at ignored pixels
+    am_ref = c_oracle.argmax(logits)
+    assert np.array_equal(am, am_ref)
+    cm_ref, _ = c_oracle.confmat(am_ref, target, C, ignore_index)
+    assert np.array_equal(cm, cm_ref)
+
+
+GOLDEN_CASES = ["cel_c7", "cel_c7_ignore0", "wcel_c7", "wcel_c7_ignore0", "cel_c16", "wcel_c16", "cel_c7_bf16vals",
+                "cel_c7_allignored", "cel_c3_odd"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("path", ["auto", "tma", "direct", "generic"])
+def test_golden_cases_fp32(golden, lib, name, path):
+    """The reference's own outputs (utils.load_loss criterion + backward) on every K1 variant."""
+    g = golden("ce_cases")
+    lib.set_option(lib.OPT_CE_PATH, PATHS[path])
+    logits, target = g[f"{name}.logits"], g[f"{name}.target"]
+    w = g[f"{name}.weight"] if g[f"{name}.weight"].size else None
+    ii = int(g[f"{name}.ignore_index"])
+    loss, sums, grad, am, cm = run_k1(logits, target, w, ii)
+    loss_ref, grad_ref = float(g[f"{name}.loss"]), g[f"{name}.grad"]
+    if np.isnan(loss_ref):
+        assert np.isnan(loss)
+        assert np.all(np.nan_to_num(grad) == 0)
+    else:
+        assert abs(loss - loss_ref) <= F32_TOL * abs(loss_ref)
+        assert np.abs(grad - grad_ref).max() <= F32_TOL * np.abs(grad_ref).max()
+    # forward-only mode (validation_loss under no_grad, utils.py:109-120)
+    loss2, _, grad2, am2, cm2 = run_k1(logits, target, w, ii, want_grad=False)
+    assert grad2 is None and (loss2 == loss or (np.isnan(loss) and np.isnan(loss2)))
+    _, am_ref = torch.max(torch.from_numpy(logits), dim=1)
+    assert np.array_equal(am, am_ref.numpy()) and np.array_equal(am2, am)
+    assert np.array_equal(cm, cm2)
+    check_against(loss, grad, am, cm, logits, target, w, ii, F32_TOL)
+
+
+@pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
+@pytest.mark.parametrize("label_dtype", [torch.uint8, torch.int64])
+@pytest.mark.parametrize("C", [2, 5, 7, 8, 12, 16, 20, 21, 33])
+def test_random_fp32(lib, layout, label_dtype, C):
+    g = torch.Generator().manual_seed(C)
+    B, H, W = 3, 48, 80
+    logits = (torch.randn(B, C, H, W, generator=g) * 3).numpy()
+    target = torch.randint(0, C, (B, H, W), generator=g).numpy().astype(np.int64)
+    target[0, :5] = 255                                    # LoveDA-style ignore label
+    weight = (torch.rand(C, generator=g) + 0.1).numpy()
+    weight[C // 2] = 0.0                                   # zero-weight class
+    am_dtype = torch.int64 if label_dtype == torch.int64 else torch.uint8
+    loss, sums, grad, am, cm = run_k1(logits, target, weight, 255, layout=layout, label_dtype=label_dtype,
+                                      argmax_dtype=am_dtype)
+    check_against(loss, grad, am, cm, logits, target, weight, 255, F32_TOL)
+    assert sums[2] == 0
+    # the library call the reference makes, on the same inputs
+    l_t, g_t = torch_path.ce_loss_and_grad(torch.from_numpy(logits), torch.from_numpy(target),
+                                           torch.from_numpy(weight), 255)
+    assert abs(loss - float(l_t)) <= F32_TOL * abs(float(l_t))
+    assert np.abs(grad - g_t.numpy()).max() <= F32_TOL * np.abs(g_t.numpy()).max()
+
+
+@pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
+@pytest.mark.parametrize("path", ["auto", "direct", "generic"])
+@pytest.mark.parametrize("C", [7, 12, 13, 20])
+def test_random_bf16(lib, layout, path, C):
+    """cfg3: bf16 logits, class weights, ignore_index=255.  Oracle = fp32 CE on the same bf16 values."""
+    lib.set_option(lib.OPT_CE_PATH, PATHS[path])
+    g = torch.Generator().manual_seed(100 + C)
+    B, H, W = 2, 64, 64
+    logits = (torch.randn(B, C, H, W, generator=g) * 3).to(torch.bfloat16).float().numpy()
+    target = torch.randint(0, C, (B, H, W), generator=g).numpy().astype(np.int64)
+    target[torch.rand(B, H, W, generator=g).numpy() < 0.1] = 255
+    weight = (torch.rand(C, generator=g) + 0.1).numpy()
+    loss, sums, grad, am, cm = run_k1(logits, target, weight, 255, layout=layout, dtype=torch.bfloat16)
+    l_ref, _, g_ref = c_oracle.cross_entropy(logits, target, weight, 255)
+    assert abs(loss - l_ref) <= F32_TOL * abs(l_ref)              # the loss itself is computed in fp32
+    assert np.abs(grad - g_ref).max() <= BF16_TOL * np.abs(g_ref).max()
+    am_ref = c_oracle.argmax(logits)
+    assert np.array_equal(am, am_ref)                              # argmax on bf16 values is exact
+    assert np.array_equal(cm, c_oracle.confmat(am_ref, target, C, 255)[0])
+    # bf16 gradients are the fp32 gradients rounded once (RNE)
+    g32 = torch.from_numpy(g_ref).to(torch.bfloat16).float().numpy()
+    assert np.abs(grad - g32).max() <= 2.0 ** -7 * np.abs(g_ref).max()
+
+
+def test_special_values_and_ties(golden, lib):
+    g = golden("argmax_cases")
+    small = g["small"][None]                                       # [1,C,H,W] with NaN / inf / ties
+    target = np.zeros((1, 2, 4), np.int64)
+    for path in ("auto", "direct", "generic"):
+        lib.set_option(lib.OPT_CE_PATH, PATHS[path])
+        loss, _, _, am, cm = run_k1(small, target, None, -100, want_grad=False)
+        assert np.array_equal(am[0], g["small_max"])
+        assert np.isnan(loss)                                      # NaN logits poison the mean, as in torch
+        big = g["big"][None]
+        tb = np.zeros((1, 24, 40), np.int64)
+        _, _, _, amb, _ = run_k1(big, tb, None, -100, want_grad=False)
+        assert np.array_equal(amb[0], g["big_max"])
+
+
+def test_out_of_bounds_label_poisons_loss(lib):
+    logits = np.zeros((1, 7, 16, 16), np.float32)
+    target = np.zeros((1, 16, 16), np.int64)
+    target[0, 3, 3] = 7
+    target[0, 4, 4] = 200
+    for dt in (torch.uint8, torch.int64):
+        loss, sums, grad, am, cm = run_k1(logits, target, None, -100, label_dtype=dt)
+        assert np.isnan(loss) and sums[2] == 2
+        assert cm.sum() == 16 * 16 - 2
+    target[0, 5, 5] = -1
+    loss, sums, *_ = run_k1(logits, target, None, -100, label_dtype=torch.int64)
+    assert sums[2] == 3
+    # workspace is left clean: the next call is unaffected
+    target[:] = 1
+    loss, sums, *_ = run_k1(logits, target, None, -100)
+    assert sums[2] == 0 and abs(loss - np.log(7)) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(1, 7, 1, 16), (2, 7, 3, 16), (1, 7, 50, 50), (2, 7, 225, 225), (1, 3, 1, 1),
+                                   (5, 7, 40, 40), (1, 7, 1040, 16)])
+def test_ragged_shapes(lib, shape):
+    """Chunk tails, plane sizes that are not multiples of 16 (falls back to direct / generic)."""
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(H * W)
+    logits = torch.randn(B, C, H, W, generator=g).numpy()
+    target = torch.randint(0, C, (B, H, W), generator=g).numpy().astype(np.int64)
+    for layout in ("NCHW", "NHWC"):
+        loss, sums, grad, am, cm = run_k1(logits, target, None, 0, layout=layout)
+        check_against(loss, grad, am, cm, logits, target, None, 0, F32_TOL)
+
+
+@pytest.mark.parametrize("stages", [2, 3])
+def test_tma_pipeline_depths(lib, stages):
+    lib.set_option(lib.OPT_CE_PATH, PATHS["tma"])
+    lib.set_option(lib.OPT_TMA_STAGES, stages)
+    g = torch.Generator().manual_seed(7)
+    B, C, H, W = 4, 7, 256, 256                                  # 256 chunks of 1024 px
+    logits = torch.randn(B, C, H, W, generator=g).numpy()
+    target = torch.randint(0, C, (B, H, W), generator=g).numpy().astype(np.int64)
+    loss, sums, grad, am, cm = run_k1(logits, target, None, 0)
+    check_against(loss, grad, am, cm, logits, target, None, 0, F32_TOL)
+
+
+def test_run_to_run_bit_stable(lib):
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(4, 7, 128, 128, generator=g).numpy()
+    target = torch.randint(0, 7, (4, 128, 128), generator=g).numpy().astype(np.int64)
+    a = run_k1(logits, target, None, 0)
+    b = run_k1(logits, target, None, 0)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("dtype,C,B", [(torch.float32, 7, 16), (torch.bfloat16, 7, 16), (torch.float32, 20, 4)])
+def test_full_size_properties(lib, dtype, C, B):
+    """BASELINE.json sizes (B x C x 1024 x 1024): size-independent invariants on the GPU results, and the
+    loss / confusion matrix against the oracle (argmax + confusion on the CPU take seconds)."""
+    from cvcs_b200 import ops
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    H = W = 1024
+    logits_cpu = (torch.randn(B, C, H, W, generator=g) * 3).to(dtype)
+    target_cpu = torch.randint(0, C, (B, H // 32, W // 32), generator=g, dtype=torch.uint8)
+    target_cpu = target_cpu.repeat_interleave(32, 1).repeat_interleave(32, 2).contiguous()   # blocky labels
+    target_cpu[torch.rand(B, H, W, generator=g) < 0.1] = 255
+    weight_cpu = torch.rand(C, generator=g) + 0.5
+    x, t, w = logits_cpu.to(dev), target_cpu.to(dev), weight_cpu.to(dev)
+    tw = torch.empty(2, dtype=torch.float64, device=dev)
+    hist = torch.zeros(C + 2, dtype=torch.int64, device=dev)
+    ops.label_hist(t, C, 255, hist=hist, weight=w, total_weight_out=tw)
+    am = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
+    loss, sums, d = ops.ce_fused(x, t, w, 255, want_grad=True, inv_total_weight_dev=tw[1:], argmax=am, confmat=cm)
+    torch.cuda.synchronize()
+    hist_c, cm_c, sums_c = hist.cpu(), cm.cpu(), sums.cpu()
+    n_valid = int((target_cpu != 255).sum())
+    # (1) label histogram == bincount, ignored bucket == #255
+    assert torch.equal(hist_c[:C], torch.bincount(target_cpu[target_cpu != 255].long().flatten(), minlength=C))
+    assert int(hist_c[C]) == B * H * W - n_valid and int(hist_c[C + 1]) == 0
+    # (2) every valid pixel lands in exactly one bin; row sums are the label histogram
+    assert int(cm_c.sum()) == n_valid and torch.equal(cm_c.sum(1), hist_c[:C])
+    # (3) Σw from the kernel == Σw from the histogram == K4's total weight
+    sw = float((hist_c[:C].double() * weight_cpu.double()).sum())
+    assert abs(sums_c[1].item() - sw) <= 1e-9 * sw and abs(tw[0].item() - sw) <= 1e-12 * sw
+    # (4) per-pixel gradients sum to ~0 over classes, and are exactly 0 at ignored pixels
+    ds = d.float().sum(1)
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    assert float(ds.abs().max()) <= tol * float(d.float().abs().max())
+    assert float(d.float().abs().amax(1)[t == 255].max()) == 0.0
+    # (5) column sums of the confusion matrix == histogram of the argmax map over valid pixels
+    amv = am[t != 255].long()
+    assert torch.equal(cm_c.sum(0), torch.bincount(amv, minlength=C).cpu())
+    # (6) against the reference's library calls on the host
+    xf = logits_cpu.float()
+    l_ref = torch_path.ce_loss_only(xf, target_cpu.long(), weight_cpu, 255)
+    assert abs(loss.item() - l_ref.item()) <= F32_TOL * abs(l_ref.item())
+    _, am_ref = torch.max(xf, dim=1)
+    assert torch.equal(am.cpu().long(), am_ref)
+    ref_cm = torch_path.RestatedConfusionMatrix(C, ignore_index=255)
+    ref_cm.update(am_ref, target_cpu.long())
+    assert torch.equal(cm_c, ref_cm.compute())
+    # (7) gradient parity on the first image (fp32 autograd on the CPU)
+    inv = 1.0 / sums_c[1].item()
+    x0 = xf[:1].clone().requires_grad_(True)
+    l0 = torch.nn.functional.cross_entropy(x0, target_cpu[:1].long(), weight_cpu, ignore_index=255, reduction="sum")
+    l0.backward()
+    g0 = (x0.grad * inv).numpy()
+    gt = d[:1].float().cpu().numpy()
+    assert np.abs(gt - g0).max() <= (F32_TOL if dtype == torch.float32 else BF16_TOL) * np.abs(g0).max()

@@ -1,0 +1,216 @@
+"""K2 / K3 / K4 / K5 and the N2-N4 kernels through the C-ABI: bit-exact against the oracle and
+the reference-generated golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, torch_path
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int64])
+@pytest.mark.parametrize("C,ignore", [(7, -100), (7, 255), (7, 0), (16, 0), (20, 255), (100, 255)])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 4099, 1 << 20])
+def test_label_hist(dtype, C, ignore, n):
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(n + C)
+    lab = torch.randint(0, C, (n,), generator=g, dtype=torch.uint8)
+    if n > 3:
+        lab[::7] = 255
+        lab[3] = C  # out of bounds (C <= 255 here)
+    ref = c_oracle.label_hist(lab.numpy(), C, ignore)
+    w = torch.rand(C, generator=g) + 0.1
+    hist = torch.ones(C + 2, dtype=torch.int64, device=DEV)     # accumulated INTO
+    tw = torch.zeros(2, dtype=torch.float64, device=DEV)
+    ops.label_hist(lab.to(DEV).to(dtype), C, ignore, hist=hist, weight=w.to(DEV), total_weight_out=tw)
+    assert np.array_equal(hist.cpu().numpy() - 1, ref)
+    sw = sum(float(ref[c]) * float(w[c]) for c in range(C) if c != ignore)
+    assert abs(tw[0].item() - sw) <= 1e-12 * max(sw, 1)
+    tw2 = ops.total_weight(hist - 1, w.to(DEV), C, ignore)
+    assert tw2[0].item() == pytest.approx(sw, rel=1e-12) and (sw == 0 or tw2[1].item() == pytest.approx(1 / sw, rel=1e-12))
+
+
+def test_label_hist_matches_reference_class_counts(golden):
+    from cvcs_b200 import ops
+    from cvcs_b200.loss import class_weights_from_counts
+    g = golden("dataset_cases")
+    hist = torch.zeros(18, dtype=torch.int64, device=DEV)
+    for k in (0, 1):
+        ops.label_hist(torch.from_numpy(g[f"scene{k}.label"]).to(DEV), 16, -100, hist=hist)
+    counts = hist[:16].cpu()
+    assert np.array_equal(counts.numpy().astype(np.float32), g["counts"])
+    assert np.array_equal(class_weights_from_counts(counts, False).numpy(), g["weights_ib0"])
+    assert np.array_equal(class_weights_from_counts(counts, True).numpy(), g["weights_ib1"])
+
+
+@pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 7, 64, 64), (1, 16, 33, 17), (3, 20, 32, 48), (1, 1, 8, 8), (1, 300, 4, 4)])
+def test_argmax(layout, dtype, shape):
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).to(dtype)
+    x[:, :, ::2, ::3] = x[:, :1, ::2, ::3]                       # ties across all classes -> index 0
+    xd = x.to(DEV)
+    if layout == "NHWC":
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    _, ref = torch.max(x.float(), dim=1)                          # utils.py:90 semantics
+    out64 = ops.argmax(xd, torch.int64)
+    assert torch.equal(out64.cpu(), ref)
+    if shape[1] <= 256:
+        assert torch.equal(ops.argmax(xd, torch.uint8).cpu().long(), ref)
+
+
+def test_argmax_special_values(golden):
+    from cvcs_b200 import ops
+    g = golden("argmax_cases")
+    x = torch.from_numpy(g["small"])[None].to(DEV)
+    assert np.array_equal(ops.argmax(x)[0].cpu().numpy(), g["small_max"])
+    hwc = x.contiguous(memory_format=torch.channels_last)         # utils.py:158 reads HWC
+    assert np.array_equal(ops.argmax(hwc)[0].cpu().numpy(), g["small_argmax_hwc"])
+    assert np.array_equal(ops.argmax(torch.from_numpy(g["big"])[None].to(DEV))[0].cpu().numpy(), g["big_max"])
+
+
+@pytest.mark.parametrize("pd,td", [(torch.uint8, torch.uint8), (torch.int64, torch.int64), (torch.uint8, torch.int64)])
+@pytest.mark.parametrize("C,ignore", [(2, None), (7, None), (7, 0), (16, 0), (20, 255), (150, None)])
+@pytest.mark.parametrize("n", [0, 5, 4096, 100003])
+def test_confmat(pd, td, C, ignore, n):
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(n + C)
+    hi = min(C, 255)
+    p = torch.randint(0, hi, (n,), generator=g)
+    t = torch.randint(0, hi, (n,), generator=g)
+    t = (t // 3) * 3 % hi                                          # runs of identical labels
+    if ignore == 255 and n:
+        t[::5] = 255
+    ref, _ = c_oracle.confmat(p.numpy(), t.numpy(), C, ignore)
+    cm = torch.zeros((C, C), dtype=torch.int64, device=DEV)
+    st = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ops.confmat_update(cm, p.to(pd).to(DEV), t.to(td).to(DEV), C, ignore, status=st)
+    ops.confmat_update(cm, p.to(pd).to(DEV), t.to(td).to(DEV), C, ignore, status=st)   # accumulates
+    assert np.array_equal(cm.cpu().numpy(), 2 * ref)
+    assert int(st.item()) == 0
+
+
+def test_confmat_flags_out_of_range():
+    from cvcs_b200 import ops
+    cm = torch.zeros((7, 7), dtype=torch.int64, device=DEV)
+    st = torch.zeros(1, dtype=torch.int64, device=DEV)
+    p = torch.tensor([0, 7, 3, 2], dtype=torch.int64, device=DEV)
+    t = torch.tensor([0, 1, 9, 2], dtype=torch.int64, device=DEV)
+    ops.confmat_update(cm, p, t, 7, None, status=st)
+    assert int(st.item()) == 2 and int(cm.sum()) == 2
+
+
+def test_eval_golden_through_k2_k3(golden):
+    """utils.eval_model's matrices (reference-generated) via argmax + confusion kernels."""
+    from cvcs_b200 import ops
+    g = golden("eval_cases")
+    x = torch.from_numpy(g["logits"]).to(DEV)
+    y = torch.from_numpy(g["labels"]).to(DEV)
+    for ib in (0, 1):
+        cm = torch.zeros((16, 16), dtype=torch.int64, device=DEV)
+        for i in range(x.shape[0]):                               # tile by tile, as the reference loops
+            pred = ops.argmax(x[i:i + 1])
+            ops.confmat_update(cm, pred, y[i:i + 1], 16, 0 if ib else None)
+        assert np.array_equal(cm.cpu().numpy(), g[f"ib{ib}.flat"])
+
+
+# ---- K5 --------------------------------------------------------------------------------------------
+def test_tile_reference_crops(golden):
+    from cvcs_b200 import ops
+    g = golden("dataset_cases")
+    img = torch.from_numpy(g["crop.image"]).to(DEV)
+    msk = torch.from_numpy(g["crop.mask"][0]).to(DEV)
+    for i, (tly, tlx, q) in enumerate(g["crop.cases"]):
+        yx = torch.tensor([[tly, tlx]], dtype=torch.int32, device=DEV)
+        out, lab = ops.tile_normalize(img, yx, (int(q), int(q)), out_dtype=torch.uint8, label=msk)
+        assert np.array_equal(out[0].cpu().numpy(), g[f"crop.{i}.patch"])
+        assert np.array_equal(lab[0].cpu().numpy(), g[f"crop.{i}.mask"][0])
+    out, _ = ops.tile_normalize(img, torch.tensor([[0, 0], [-2, -2]], dtype=torch.int32, device=DEV), (6, 6),
+                                out_dtype=torch.uint8)
+    assert np.array_equal(out[0].cpu().numpy(), g["padded.patch"])      # _get_padded_patch(img, 2, 2, (4,4), 6)
+    assert np.array_equal(out[1].cpu().numpy(), g["padded.corner"])
+
+
+def test_tile_loader_order_cast_and_normalize(golden):
+    from cvcs_b200 import ops
+    g = golden("dataset_cases")
+    p, cols, tpi = 224, 2, 2
+    for tag in ("shift0",):
+        for k, idx in enumerate(g[f"{tag}.chunk_crops"]):
+            im, tly, tlx = torch_path.tile_top_left(int(idx), tpi, cols, p)
+            scene = torch.from_numpy(g[f"scene{im}.image"]).to(DEV)
+            lab = torch.from_numpy(g[f"scene{im}.label"]).to(DEV)
+            yx = torch.tensor([[tly, tlx]], dtype=torch.int32, device=DEV)
+            out, lo = ops.tile_normalize(scene, yx, (p, p), out_dtype=torch.uint8, label=lab)
+            assert np.array_equal(out[0].cpu().numpy(), g[f"{tag}.patches"][k])
+            assert np.array_equal(lo[0].cpu().numpy(), g[f"{tag}.index_masks"][k])
+    allv = torch.from_numpy(g["normalize.in"]).to(DEV)
+    yx = torch.zeros((1, 2), dtype=torch.int32, device=DEV)
+    mean = torch.tensor([0.485, 0.456, 0.406], device=DEV)
+    std = torch.tensor([0.229, 0.224, 0.225], device=DEV)
+    out, _ = ops.tile_normalize(allv, yx, (16, 16), mean, std)
+    assert np.array_equal(out[0].cpu().numpy(), g["normalize.out"])      # bit-exact fp32 (nets.py:339-342)
+    out, _ = ops.tile_normalize(allv, yx, (16, 16))
+    assert np.array_equal(out[0].cpu().numpy(), g["cast.out"])           # train.py:121
+    outb, _ = ops.tile_normalize(allv, yx, (16, 16), mean, std, out_dtype=torch.bfloat16)
+    assert torch.equal(outb[0].cpu(), torch.from_numpy(g["normalize.out"]).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("Cb,H,W,p", [(3, 300, 500, 224), (13, 520, 1030, 256), (4, 100, 100, 37), (1, 64, 64, 64)])
+def test_tile_random_multiband(Cb, H, W, p):
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(Cb * H)
+    scene = torch.randint(0, 256, (Cb, H, W), generator=g, dtype=torch.uint8)
+    lab = torch.randint(0, 20, (H, W), generator=g, dtype=torch.uint8)
+    rows, cols = torch_path.tiles_in_image(H, W, p)
+    yx = [(r * p, c * p) for r in range(rows) for c in range(cols)]
+    yx += [(-5, -7), (H - p // 2, W - p // 2), (3, 1)]               # shifted / overhanging tiles
+    yx = np.array(yx, dtype=np.int32)
+    mean = (torch.rand(Cb, generator=g) * 100).numpy().astype(np.float32)
+    std = (torch.rand(Cb, generator=g) * 50 + 1).numpy().astype(np.float32)
+    ref, ref_lab = c_oracle.tile(scene.numpy(), yx, p, p, mean, std, labels=lab.numpy())
+    hist = torch.zeros(22, dtype=torch.int64, device=DEV)
+    out, lo = ops.tile_normalize(scene.to(DEV), torch.from_numpy(yx).to(DEV), (p, p), torch.from_numpy(mean).to(DEV),
+                                 torch.from_numpy(std).to(DEV), label=lab.to(DEV), hist=hist, hist_classes=20)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert np.array_equal(lo.cpu().numpy(), ref_lab)
+    assert np.array_equal(hist.cpu().numpy(), c_oracle.label_hist(ref_lab, 20))
+    out64, lo64 = ops.tile_normalize(scene.to(DEV), torch.from_numpy(yx).to(DEV), (p, p), label=lab.to(DEV),
+                                     label_out_dtype=torch.int64)
+    assert np.array_equal(lo64.cpu().numpy(), ref_lab.astype(np.int64))
+    assert np.array_equal(out64.cpu().numpy(), c_oracle.tile(scene.numpy(), yx, p, p)[0])
+
+
+# ---- N2 / N3 / N4 ----------------------------------------------------------------------------------
+def test_vote_colorize_stitch(golden):
+    from cvcs_b200 import ops
+    g = golden("misc_cases")
+    for n in (2, 3, 4, 5):
+        maps = torch.from_numpy(g[f"vote{n}.in"]).to(DEV)
+        assert np.array_equal(ops.vote(maps).cpu().numpy(), g[f"vote{n}.out"])          # torch.mode (utils.py:506)
+        assert np.array_equal(ops.vote(maps.to(torch.uint8)).cpu().numpy(), g[f"vote{n}.out"])
+    out = ops.colorize(torch.from_numpy(g["iconvert.in"]).to(DEV), torch.from_numpy(g["iconvert.lut"]).to(DEV))
+    assert np.array_equal(out.cpu().numpy(), g["iconvert.out"])                        # converters.py:23-36
+    tiles = torch.arange(2 * 6 * 6, dtype=torch.uint8).reshape(2, 6, 6)
+    yx = torch.tensor([[0, 0], [0, 4]], dtype=torch.int32)
+    scene = ops.stitch(tiles.to(DEV), yx.to(DEV), (4, 8), crop_hw=(4, 4))
+    assert np.array_equal(scene.cpu().numpy(), c_oracle.stitch(tiles.numpy(), yx.numpy(), 4, 8, crop=(4, 4)))
+
+
+def test_tile_argmax_stitch_roundtrip():
+    """Size-independent property: tiling a label scene and stitching the tiles back is the identity
+    on the covered area (remainder rows/cols dropped, dataset.py:63,125)."""
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    H, W, p = 1000, 1300, 224
+    lab = torch.randint(0, 16, (H, W), generator=g, dtype=torch.uint8).to(DEV)
+    rows, cols = H // p, W // p
+    yx = torch.tensor([(r * p, c * p) for r in range(rows) for c in range(cols)], dtype=torch.int32, device=DEV)
+    tiles, _ = ops.tile_normalize(lab[None], yx, (p, p), out_dtype=torch.uint8)
+    back = ops.stitch(tiles[:, 0].contiguous(), yx, (H, W))
+    assert torch.equal(back[:rows * p, :cols * p], lab[:rows * p, :cols * p])
+    assert int(back[rows * p:].sum()) == 0 and int(back[:, cols * p:].sum()) == 0
