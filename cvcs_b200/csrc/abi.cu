@@ -298,7 +298,8 @@ int cvcs_host_ce_fused(cvcs_host_ctx* c, const void* logits, int logits_dtype, i
         CVCS_CUDA_OK(cudaStreamWaitEvent(c->s_comp, c->ev_in[k], 0));
         int rc = ce_fused_launch(static_cast<char*>(c->d_logits) + loff, logits_dtype, layout,
                                  static_cast<char*>(c->d_target) + static_cast<size_t>(hw) * b0 * tsize, target_dtype,
-                                 weight ? c->d_weight : nullptr, ignore_index, nb, C, H, W, 0.0, c->d_tw,
+                                 weight ? c->d_weight : nullptr, ignore_index, nb, C, H, W, 0.0,
+                                 want_grad ? c->d_tw + 1 : nullptr,  // {Σw, 1/Σw}: K1 wants the reciprocal
                                  want_grad ? static_cast<char*>(c->d_dlogits) + loff : nullptr,
                                  static_cast<char*>(c->d_argmax) + static_cast<size_t>(hw) * b0 * asize, argmax_dtype,
                                  c->d_conf, c->d_sums + 3 * k, nullptr, c->d_ws, c->s_comp);

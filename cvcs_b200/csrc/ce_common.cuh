@@ -29,6 +29,7 @@ struct CeParams {
     int C;
     int target_i64;  // 0: u8, 1: i64
     int argmax_i64;  // 0: u8, 1: i64
+    int conf_reps;   // generic kernel: shared-memory replicas of the C*C bins (0 = global atomics)
 };
 
 // launchers (one translation unit each)
@@ -141,7 +142,7 @@ __device__ __forceinline__ int pixel_ce(float (&x)[C], int tv, const float* __re
     step_l += valid ? w * nll : 0.f;
     step_w += w;
     if (do_grad) {
-        const float gsc = w * inv_tw;  // 0 at ignored pixels -> exact zeros, as autograd gives
+        const float gsc = valid ? w * inv_tw : 0.f;  // exact zeros at ignored pixels even when 1/Σw = inf
         const float r = __fdividef(gsc, s);
 #pragma unroll
         for (int c = 0; c < C; ++c) x[c] = fmaf(x[c], r, (c == tv) ? -gsc : 0.f);

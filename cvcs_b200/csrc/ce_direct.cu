@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) ce_generic_kernel(const CeParams p, 
     float* wsm = reinterpret_cast<float*>(smem);
     for (int c = threadIdx.x; c < C; c += kThreads) wsm[c] = p.weight ? p.weight[c] : 1.0f;
     BinAcc<false> conf;
-    if (do_conf) conf.init(smem + ((C * 4 + 15) / 16) * 16, C * C);
+    if (do_conf) conf.init(smem + ((C * 4 + 15) / 16) * 16, C * C, p.conf_reps, p.confmat);
     else __syncthreads();
     const float inv_tw = do_grad ? static_cast<float>(p.inv_tw_dev ? *p.inv_tw_dev : p.inv_tw) : 0.f;
     const T* __restrict__ logits = reinterpret_cast<const T*>(p.logits);
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) ce_generic_kernel(const CeParams p, 
         lsum += valid ? static_cast<double>(w * nll) : 0.0;
         wsum += static_cast<double>(w);
         if (do_grad) {
-            const float gsc = w * inv_tw;
+            const float gsc = valid ? w * inv_tw : 0.f;
             const float r = __fdividef(gsc, s);
             for (int c = 0; c < C; ++c) {
                 float xc[1];
@@ -213,14 +213,14 @@ int ce_direct_launch(const CeParams& p, int logits_dtype, int vec, cudaStream_t 
     return CVCS_OK;
 }
 
-int ce_generic_launch(const CeParams& p, int logits_dtype, int layout, cudaStream_t stream) {
-    const int C = p.C;
+int ce_generic_launch(const CeParams& p0, int logits_dtype, int layout, cudaStream_t stream) {
+    const int C = p0.C;
+    CeParams p = p0;
     const long long class_stride = layout == CVCS_NCHW ? p.hw : 1;
     const long long pixel_stride = layout == CVCS_NCHW ? 1 : C;
     const long long image_stride = static_cast<long long>(C) * p.hw;
-    const int smem = ((C * 4 + 15) / 16) * 16 + (p.confmat ? BinAcc<false>::smem_bytes(C * C) : 0);
-    if (smem > 200 * 1024)
-        return set_error(CVCS_ERR_UNSUPPORTED, "C=%d: confusion matrix does not fit in shared memory", C);
+    p.conf_reps = shared_bin_replicas(C * C);
+    const int smem = ((C * 4 + 15) / 16) * 16 + (p.confmat ? BinAcc<false>::smem_bytes(C * C, p.conf_reps) : 0);
     const long long blocks_needed = (p.n_pixels + kThreads - 1) / kThreads;
     int grid = 0;
     if (logits_dtype == CVCS_F32) {

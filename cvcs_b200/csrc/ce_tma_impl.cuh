@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
 
 // ---- launch ------------------------------------------------------------------------------------
 template <typename T, int C, int VECP, bool NHWC>
-int launch(const CeParams& p0, cudaStream_t stream) {
+int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     constexpr bool PRIV = C * C <= kPrivBinsMax;
     constexpr int P = kThreads * VECP;
     constexpr int ES = sizeof(T);
@@ -354,13 +354,17 @@ int launch(const CeParams& p0, cudaStream_t stream) {
     g.hist_off = 0;
     const int hist_bytes = p.confmat ? BinAcc<PRIV>::smem_bytes(C * C) : 0;
     g.stage_off = ((hist_bytes + 127) / 128) * 128;
-    // two CTAs per SM: each may use up to ~112 KB of the 227 KB
-    const int budget = 113 * 1024 - g.stage_off;
-    int stages = budget / g.stage_bytes;
+    // two CTAs per SM: each may use up to ~112 KB of the 227 KB; wide stages (i64 labels, large C)
+    // that would leave fewer than 3 stages get the whole SM instead
+    int stages = (113 * 1024 - g.stage_off) / g.stage_bytes;
+    if (stages < 3) stages = (226 * 1024 - g.stage_off) / g.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     const int want_stages = get_option(CVCS_OPT_TMA_STAGES);
     if (want_stages >= 2 && want_stages <= kMaxStages && want_stages <= stages) stages = want_stages;
-    if (stages < 2) return set_error(CVCS_ERR_UNSUPPORTED, "tma path: stage of %d B leaves < 2 stages", g.stage_bytes);
+    if (stages < 2) {  // not even double-buffered: leave the shape to the direct / generic variants
+        *handled = false;
+        return CVCS_OK;
+    }
     g.stages = stages;
     const int smem = g.stage_off + stages * g.stage_bytes;
     auto kernel = ce_tma_kernel<T, C, VECP, NHWC, PRIV>;
@@ -387,7 +391,7 @@ int dispatch(const CeParams& p, cudaStream_t stream, bool* handled) {
     } else {
         if (p.C == CC) {
             *handled = true;
-            return launch<T, CC, VECP, NHWC>(p, stream);
+            return launch<T, CC, VECP, NHWC>(p, stream, handled);
         }
         return dispatch<T, VECP, NHWC, CLO, CHI, CC + 1>(p, stream, handled);
     }

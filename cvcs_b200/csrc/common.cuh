@@ -16,9 +16,11 @@ int get_option(int option);  // cvcs_set_option values (0 = default / auto)
 #define CVCS_CUDA_OK(expr)                                                                   \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \
-        if (_e != cudaSuccess)                                                               \
+        if (_e != cudaSuccess) {                                                             \
+            (void)cudaGetLastError(); /* do not leak a non-sticky error into the next call */ \
             return ::cvcs::set_error(CVCS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,          \
                                      cudaGetErrorString(_e), __FILE__, __LINE__);            \
+        }                                                                                    \
     } while (0)
 
 #define CVCS_REQUIRE(cond, ...)                                              \
@@ -43,6 +45,15 @@ static_assert(sizeof(Workspace) <= kWorkspaceBytes, "workspace too small");
 
 constexpr int kThreads = 256;  // CTA width of every persistent kernel
 constexpr int kWarps = kThreads / 32;
+
+// replicas of a shared-memory u32 bin array: 8 (one per warp) while that stays small, halved until
+// it fits `budget`; 0 = not even one copy fits (every hit becomes a global atomic)
+inline int shared_bin_replicas(int nbins, int budget_bytes = 64 * 1024, int hard_limit_bytes = 160 * 1024) {
+    int r = kWarps;
+    while (r > 1 && static_cast<long long>(nbins) * r * 4 > budget_bytes) r >>= 1;
+    if (static_cast<long long>(nbins) * r * 4 > hard_limit_bytes) return 0;
+    return r;
+}
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -212,7 +223,9 @@ __device__ __forceinline__ bool better(float v, float best) {
 
 // ---- shared-memory bin accumulators (confusion matrix, label histogram) ------------------------
 // Private mode: u16 cnt[bin][thread] (no atomics, no same-address serialisation however blocky the
-// label map is); shared mode: u32 bins[warp][nb] with shared-memory atomics.  CTAs are kThreads wide.
+// label map is); shared mode: u32 bins[rep][nb] with shared-memory atomics, warp w using replica
+// w % reps (reps = 8 for small matrices, fewer when C*C*4 B would not fit); reps == 0: the bins do
+// not fit shared memory at all and every hit is a 64-bit global atomic.  CTAs are kThreads wide.
 // BAR = 0: the accumulator is used by the whole CTA (__syncthreads); BAR > 0: by threads
 // 0..kThreads-1 of a wider CTA, synchronised on named barrier BAR.
 template <bool PRIV, int BAR = 0>
@@ -223,17 +236,22 @@ struct BinAcc {
     }
     unsigned short* cnt16;
     unsigned int* bins32;
+    unsigned long long* direct;
     int nb;
+    int reps;
 
-    __device__ __forceinline__ void init(unsigned char* smem, int nbins) {
+    __device__ __forceinline__ void init(unsigned char* smem, int nbins, int replicas = kWarps,
+                                         unsigned long long* global_bins = nullptr) {
         nb = nbins;
+        reps = replicas;
+        direct = global_bins;
         if constexpr (PRIV) {
             cnt16 = reinterpret_cast<unsigned short*>(smem);
             uint32_t* z = reinterpret_cast<uint32_t*>(smem);
             for (int i = threadIdx.x; i < nb * kThreads / 2; i += kThreads) z[i] = 0u;
         } else {
             bins32 = reinterpret_cast<unsigned int*>(smem);
-            for (int i = threadIdx.x; i < nb * kWarps; i += kThreads) bins32[i] = 0u;
+            for (int i = threadIdx.x; i < nb * reps; i += kThreads) bins32[i] = 0u;
         }
         sync();
     }
@@ -242,10 +260,13 @@ struct BinAcc {
             unsigned short* c = cnt16 + key * kThreads + threadIdx.x;
             *c = static_cast<unsigned short>(*c + 1);
         } else {
-            atomicAdd(bins32 + (threadIdx.x >> 5) * nb + key, 1u);
+            if (reps) atomicAdd(bins32 + ((threadIdx.x >> 5) & (reps - 1)) * nb + key, 1u);
+            else atomicAdd(direct + key, 1ull);
         }
     }
-    static __host__ __device__ int smem_bytes(int nbins) { return PRIV ? nbins * kThreads * 2 : nbins * kWarps * 4; }
+    static __host__ __device__ int smem_bytes(int nbins, int replicas = kWarps) {
+        return PRIV ? nbins * kThreads * 2 : nbins * replicas * 4;
+    }
     // CTA-wide flush to global u64 bins; leaves the counters zeroed.
     __device__ __forceinline__ void flush(unsigned long long* confmat) {
         sync();
@@ -265,8 +286,7 @@ struct BinAcc {
         } else {
             for (int b = threadIdx.x; b < nb; b += kThreads) {
                 unsigned int s = 0;
-#pragma unroll
-                for (int w = 0; w < kWarps; ++w) {
+                for (int w = 0; w < reps; ++w) {
                     s += bins32[w * nb + b];
                     bins32[w * nb + b] = 0u;
                 }

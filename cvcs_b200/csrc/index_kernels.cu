@@ -312,6 +312,7 @@ struct ConfParams {
     int C;
     int pred_i64;
     int target_i64;
+    int reps;  // shared-memory replicas of the bins (shared mode); 0 = global atomics
 };
 
 template <int VEC>
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(kThreads) confmat_kernel(const ConfParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int C = p.C;
     BinAcc<PRIV> acc;
-    acc.init(smem, C * C);
+    acc.init(smem, C * C, p.reps, p.confmat);
     unsigned int since_flush = 0, bad = 0;
     const long long nv = p.n / VEC;
     auto one = [&](long long t, long long q) {
@@ -514,7 +515,7 @@ int confmat_launch(const void* pred, int pred_dtype, const void* target, int tar
     CVCS_REQUIRE(pred_dtype == CVCS_U8 || pred_dtype == CVCS_I64, "cvcs_confmat: pred dtype tag %d (want u8/i64)", pred_dtype);
     CVCS_REQUIRE(target_dtype == CVCS_U8 || target_dtype == CVCS_I64, "cvcs_confmat: target dtype tag %d (want u8/i64)", target_dtype);
     CVCS_REQUIRE(n >= 0 && C >= 1, "cvcs_confmat: bad n/C");
-    if (C > 200) return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_confmat: C=%d > 200 (bins do not fit shared memory)", C);
+    if (C > 4096) return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_confmat: C=%d > 4096", C);
     ConfParams p{};
     p.pred = pred;
     p.target = target;
@@ -525,13 +526,14 @@ int confmat_launch(const void* pred, int pred_dtype, const void* target, int tar
     p.C = C;
     p.pred_i64 = pred_dtype == CVCS_I64;
     p.target_i64 = target_dtype == CVCS_I64;
+    p.reps = shared_bin_replicas(C * C);
     const bool vec_ok = aligned_to(pred, 16) && aligned_to(target, 16);
     const bool priv = C * C <= 64;
     int grid = 0;
     int rc;
 #define CVCS_LAUNCH_CONF(PRIV, VEC)                                                     \
     do {                                                                                \
-        const int smem = BinAcc<PRIV>::smem_bytes(C * C);                               \
+        const int smem = BinAcc<PRIV>::smem_bytes(C * C, p.reps);                       \
         const long long blocks = (n / VEC + kThreads - 1) / kThreads;                   \
         rc = grid_for(confmat_kernel<PRIV, VEC>, smem, blocks, &grid);                  \
         if (rc) return rc;                                                              \

@@ -48,8 +48,8 @@ def _as_bchw(logits: torch.Tensor, target: torch.Tensor):
 
 class _FusedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, target, module):
-        want_grad = torch.is_grad_enabled() and logits.requires_grad
+    def forward(ctx, logits, target, module, want_grad):
+        # grad mode is switched off inside Function.forward, so the caller decides want_grad
         loss, dlogits, restore = module._run(logits, target, want_grad)
         ctx.module = module
         ctx.restore = restore
@@ -71,7 +71,7 @@ class _FusedCE(torch.autograd.Function):
         elif mode == "scale":
             ops.scale_inplace(d, grad_output.to(torch.float32).reshape(1))
         # mode == "unit": trust the caller that grad_output == 1
-        return ctx.restore(d), None, None
+        return ctx.restore(d), None, None, None
 
 
 class FusedCrossEntropyLoss(nn.Module):
@@ -158,7 +158,8 @@ class FusedCrossEntropyLoss(nn.Module):
             raise IndexError("Target is out of bounds.")
 
     def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        return _FusedCE.apply(input, target, self)
+        want_grad = torch.is_grad_enabled() and input.requires_grad
+        return _FusedCE.apply(input, target, self, want_grad)
 
 
 def class_weights_from_counts(counts: torch.Tensor, ignore_background: bool = False) -> torch.Tensor:

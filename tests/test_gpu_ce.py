@@ -241,9 +241,10 @@ def test_full_size_properties(lib, dtype, C, B):
     assert int(hist_c[C]) == B * H * W - n_valid and int(hist_c[C + 1]) == 0
     # (2) every valid pixel lands in exactly one bin; row sums are the label histogram
     assert int(cm_c.sum()) == n_valid and torch.equal(cm_c.sum(1), hist_c[:C])
-    # (3) Σw from the kernel == Σw from the histogram == K4's total weight
+    # (3) Σw from the kernel == Σw from the histogram == K4's total weight (K1 adds the weights of a
+    # thread's 4-8 pixels in fp32 before the fp64 accumulation: 1e-7; K4 is integer counts x fp64: 1e-12)
     sw = float((hist_c[:C].double() * weight_cpu.double()).sum())
-    assert abs(sums_c[1].item() - sw) <= 1e-9 * sw and abs(tw[0].item() - sw) <= 1e-12 * sw
+    assert abs(sums_c[1].item() - sw) <= 1e-7 * sw and abs(tw[0].item() - sw) <= 1e-12 * sw
     # (4) per-pixel gradients sum to ~0 over classes, and are exactly 0 at ignored pixels
     ds = d.float().sum(1)
     tol = 1e-6 if dtype == torch.float32 else 2e-2
