@@ -54,7 +54,7 @@ SIGNATURES = {
     "cvcs_scale_inplace": (_i, [_vp, _i, _ll, _vp, _vp]),
     "cvcs_argmax": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "cvcs_confmat": (_i, [_vp, _i, _vp, _i, _ll, _i, _ll, _vp, _vp, _vp, _vp]),
-    "cvcs_tile_normalize": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _ll,
+    "cvcs_tile_normalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _ll,
                                  _vp, _vp]),
     "cvcs_vote": (_i, [_vp, _i, _i, _ll, _i, _vp, _i, _vp]),
     "cvcs_colorize": (_i, [_vp, _i, _ll, _vp, _i, _vp, _vp]),

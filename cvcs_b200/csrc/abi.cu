@@ -45,7 +45,7 @@ int scale_launch(void*, int, long long, const float*, cudaStream_t);
 int argmax_launch(const void*, int, int, int, int, int, int, void*, int, cudaStream_t);
 int confmat_launch(const void*, int, const void*, int, long long, int, long long, unsigned long long*,
                    unsigned long long*, void*, cudaStream_t);
-int tile_launch(const unsigned char*, int, int, int, const int*, int, int, int, const float*, const float*, void*, int,
+int tile_launch(const unsigned char*, int, int, int, const int*, const int*, int, int, int, const float*, const float*, void*, int,
                 const unsigned char*, void*, int, unsigned long long*, int, long long, void*, cudaStream_t);
 int stitch_launch(const unsigned char*, int, int, int, const int*, int, int, unsigned char*, int, int, cudaStream_t);
 int vote_launch(const void*, int, int, long long, int, void*, int, cudaStream_t);
@@ -151,12 +151,13 @@ int cvcs_confmat(const void* pred_dev, int pred_dtype, const void* target_dev, i
                           status_dev, workspace_dev, static_cast<cudaStream_t>(stream));
 }
 
-int cvcs_tile_normalize(const unsigned char* scene_dev, int Cb, int H, int W, const int* tile_yx_dev, int n_tiles,
+int cvcs_tile_normalize(const unsigned char* scene_dev, int Cb, int H, int W, const int* tile_yx_dev,
+                        const int* tile_slot_dev, int n_tiles,
                         int tile_h, int tile_w, const float* mean_dev, const float* std_dev, void* out_dev,
                         int out_dtype, const unsigned char* label_dev, void* label_out_dev, int label_out_dtype,
                         unsigned long long* hist_dev, int hist_C, long long hist_ignore_index, void* workspace_dev,
                         void* stream) {
-    return tile_launch(scene_dev, Cb, H, W, tile_yx_dev, n_tiles, tile_h, tile_w, mean_dev, std_dev, out_dev, out_dtype,
+    return tile_launch(scene_dev, Cb, H, W, tile_yx_dev, tile_slot_dev, n_tiles, tile_h, tile_w, mean_dev, std_dev, out_dev, out_dtype,
                        label_dev, label_out_dev, label_out_dtype, hist_dev, hist_C, hist_ignore_index, workspace_dev,
                        static_cast<cudaStream_t>(stream));
 }

@@ -15,6 +15,7 @@ namespace {
 struct TileParams {
     const unsigned char* scene;
     const int* tile_yx;
+    const int* tile_slot;  // nullable: output slot of tile i (default i)
     const float* mean;
     const float* stdv;
     void* out;
@@ -81,11 +82,12 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileParams p) {
             const int sy = __ldg(p.tile_yx + 2 * tile) + y;
             const int sx = __ldg(p.tile_yx + 2 * tile + 1) + xg * VEC;
             const long long opix = static_cast<long long>(y) * p.tile_w + xg * VEC;  // inside a tile plane
+            const long long slot = p.tile_slot ? __ldg(p.tile_slot + tile) : static_cast<long long>(tile);
 
             for (int cb = 0; cb < p.Cb; ++cb) {
                 unsigned int px[VEC];
                 load_u8_row<VEC>(p.scene + cb * plane, p.H, p.W, sy, sx, px);
-                const long long o = (static_cast<long long>(tile) * p.Cb + cb) * tile_plane + opix;
+                const long long o = (slot * p.Cb + cb) * tile_plane + opix;
                 if (p.out_dtype == CVCS_U8) {
                     unsigned char* out = reinterpret_cast<unsigned char*>(p.out) + o;
                     if constexpr (VEC == 4) {
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileParams p) {
             if (p.label) {
                 unsigned int lb[VEC];
                 load_u8_row<VEC>(p.label, p.H, p.W, sy, sx, lb);
-                const long long o = static_cast<long long>(tile) * tile_plane + opix;
+                const long long o = slot * tile_plane + opix;
                 if (p.label_out) {
                     if (p.label_out_i64) {
                         long long* out = reinterpret_cast<long long*>(p.label_out) + o;
@@ -242,7 +244,7 @@ int simple_grid(long long n) {
 
 }  // namespace
 
-int tile_launch(const unsigned char* scene, int Cb, int H, int W, const int* tile_yx, int n_tiles, int tile_h,
+int tile_launch(const unsigned char* scene, int Cb, int H, int W, const int* tile_yx, const int* tile_slot, int n_tiles, int tile_h,
                 int tile_w, const float* mean, const float* stdv, void* out, int out_dtype,
                 const unsigned char* label, void* label_out, int label_out_dtype, unsigned long long* hist,
                 int hist_C, long long hist_ignore, void* workspace, cudaStream_t stream) {
@@ -266,6 +268,7 @@ int tile_launch(const unsigned char* scene, int Cb, int H, int W, const int* til
     TileParams p{};
     p.scene = scene;
     p.tile_yx = tile_yx;
+    p.tile_slot = tile_slot;
     p.mean = mean;
     p.stdv = stdv;
     p.out = out;

@@ -176,22 +176,38 @@ def tile_normalize(scene: torch.Tensor, tile_yx: torch.Tensor, tile_hw: Tuple[in
                    mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None,
                    out_dtype: torch.dtype = torch.float32, label: Optional[torch.Tensor] = None,
                    label_out_dtype: torch.dtype = torch.uint8, hist: Optional[torch.Tensor] = None,
-                   hist_classes: int = 0, hist_ignore_index: int = -100):
-    """scene u8 [Cb,H,W] -> tiles [n,Cb,th,tw] (cast / normalised), label u8 [H,W] -> [n,th,tw]."""
-    dev = _need_cuda(scene, tile_yx, mean, std, label, hist)
+                   hist_classes: int = 0, hist_ignore_index: int = -100, *,
+                   slots: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                   label_out: Optional[torch.Tensor] = None):
+    """scene u8 [Cb,H,W] -> tiles [n,Cb,th,tw] (cast / normalised), label u8 [H,W] -> [n,th,tw].
+
+    ``slots`` (int32 [n]) scatters tile i to ``out[slots[i]]`` of a caller-provided batch (``out`` /
+    ``label_out``), so the tiles of several scenes can be laid down in one batch in any order."""
+    dev = _need_cuda(scene, tile_yx, mean, std, label, hist, slots, out, label_out)
     assert scene.dtype == torch.uint8 and scene.dim() == 3 and scene.is_contiguous()
     assert tile_yx.dtype == torch.int32 and tile_yx.dim() == 2 and tile_yx.shape[1] == 2 and tile_yx.is_contiguous()
     Cb, H, W = scene.shape
     th, tw = tile_hw
     n = tile_yx.shape[0]
-    out = torch.empty((n, Cb, th, tw), dtype=out_dtype, device=dev)
-    label_out = None
+    if slots is not None:
+        assert slots.dtype == torch.int32 and slots.numel() == n and slots.is_contiguous()
+        assert out is not None, "slots need a caller-provided output batch"
+    if out is None:
+        out = torch.empty((n, Cb, th, tw), dtype=out_dtype, device=dev)
+    else:
+        assert out.is_contiguous() and tuple(out.shape[1:]) == (Cb, th, tw) and (slots is not None or out.shape[0] >= n)
     if label is not None:
         assert label.dtype == torch.uint8 and tuple(label.shape[-2:]) == (H, W) and label.is_contiguous()
-        label_out = torch.empty((n, th, tw), dtype=label_out_dtype, device=dev)
+        if label_out is None:
+            assert slots is None, "slots need a caller-provided label batch"
+            label_out = torch.empty((n, th, tw), dtype=label_out_dtype, device=dev)
+        else:
+            assert label_out.is_contiguous() and tuple(label_out.shape[1:]) == (th, tw)
+    else:
+        label_out = None
     with torch.cuda.device(dev):
-        check(lib.cvcs_tile_normalize(scene.data_ptr(), Cb, H, W, tile_yx.data_ptr(), n, th, tw, _ptr(mean), _ptr(std),
-                                      out.data_ptr(), _tag(out), _ptr(label), _ptr(label_out),
+        check(lib.cvcs_tile_normalize(scene.data_ptr(), Cb, H, W, tile_yx.data_ptr(), _ptr(slots), n, th, tw,
+                                      _ptr(mean), _ptr(std), out.data_ptr(), _tag(out), _ptr(label), _ptr(label_out),
                                       _tag(label_out) if label_out is not None else _lib.U8, _ptr(hist),
                                       hist_classes, hist_ignore_index, workspace(dev).data_ptr(), _stream(dev)))
     return out, label_out

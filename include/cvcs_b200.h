@@ -153,6 +153,8 @@ int cvcs_confmat(const void* pred_dev, int pred_dtype, const void* target_dev, i
  * scene_dev   u8 [Cb, H, W] (CHW, as tv_tensors.Image gives)
  * tile_yx_dev i32 [n_tiles, 2] top-left (tly, tlx) of each tile; may be negative / overhang
  *             (zero fill, torchvision crop semantics)
+ * tile_slot_dev nullable i32 [n_tiles]: tile i is written to out[tile_slot[i]] (default i), so that
+ *             the tiles of several scenes land in one batch in the chunk's shuffled order
  * tile_h/w    output tile size
  * mean_dev/std_dev  nullable f32[Cb]; out = (float(x) - mean) / std, IEEE fp32 as
  *             v2.Normalize does; both NULL -> pure cast
@@ -162,7 +164,8 @@ int cvcs_confmat(const void* pred_dev, int pred_dtype, const void* target_dev, i
  * hist_dev    nullable u64[hist_C + 2] label histogram of the emitted label tiles (same
  *             layout as cvcs_label_hist) fused into the same pass. */
 int cvcs_tile_normalize(const unsigned char* scene_dev, int Cb, int H, int W,
-                        const int* tile_yx_dev, int n_tiles, int tile_h, int tile_w,
+                        const int* tile_yx_dev, const int* tile_slot_dev, int n_tiles, int tile_h,
+                        int tile_w,
                         const float* mean_dev, const float* std_dev, void* out_dev, int out_dtype,
                         const unsigned char* label_dev, void* label_out_dev, int label_out_dtype,
                         unsigned long long* hist_dev, int hist_C, long long hist_ignore_index,
