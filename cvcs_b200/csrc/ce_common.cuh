@@ -111,39 +111,84 @@ __device__ __forceinline__ void store_argmax(const CeParams& p, long long pix, c
     }
 }
 
-// One pixel: x[0..C) holds the logits on entry and (if do_grad) the gradients on exit.
-// Returns the argmax; accumulates the loss terms.  tv uses the label encoding above.
-template <int C>
-__device__ __forceinline__ int pixel_ce(float (&x)[C], int tv, const float* __restrict__ wsm, float inv_tw,
-                                        bool do_grad, float& step_l, float& step_w, unsigned int& bad) {
-    float best = x[0], m = x[0];
+// ---- per-pixel arithmetic ------------------------------------------------------------------------
+// MUFU approximations without the range-fixing prologue/epilogue the libdevice wrappers add: the
+// arguments are range limited by construction (ex2: x - max <= 0, underflow to 0 is the right
+// answer; lg2 / rcp: Σ exp in [1, C]).  Each is one SASS instruction.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// torch.max over one pixel's classes with its NaN rule, from a fetch functor (slow path only).
+template <int C, typename F>
+__device__ __forceinline__ int argmax_nan_aware(F&& fetch) {
+    float best = fetch(0);
     int arg = 0;
 #pragma unroll
     for (int c = 1; c < C; ++c) {
-        if (better(x[c], best)) {
-            best = x[c];
+        const float v = fetch(c);
+        if (better(v, best)) {
+            best = v;
             arg = c;
         }
-        m = fmaxf(m, x[c]);
     }
+    return arg;
+}
+
+// Softmax statistics of one pixel.  On exit x[c] = exp(x[c] - max), m = max (NaNs skipped),
+// s = Σ x[c], and arg = first index with x[c] == max, which is torch's argmax whenever the row
+// holds no NaN / +inf / all -inf; those rows give s = NaN and the caller redoes the argmax with
+// argmax_nan_aware on the original values.
+template <int C>
+__device__ __forceinline__ void softmax_core(float (&x)[C], float& m, float& s, int& arg) {
+    m = x[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
+    arg = C - 1;
+#pragma unroll
+    for (int c = C - 2; c >= 0; --c) arg = (x[c] == m) ? c : arg;
+    s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        x[c] = ex2_ftz((x[c] - m) * kLog2e);
+        s += x[c];
+    }
+}
+
+// One pixel, register-only variant (direct kernels): x[0..C) holds the logits on entry and (if
+// do_grad) the gradients on exit.  Returns the argmax; accumulates the loss terms.  tv uses the
+// label encoding above.  `refetch(c)` re-reads logit c (only used for rows with NaN / inf).
+template <int C, typename F>
+__device__ __forceinline__ int pixel_ce(float (&x)[C], int tv, const float* __restrict__ wsm, float inv_tw,
+                                        bool do_grad, float& step_l, float& step_w, unsigned int& bad, F&& refetch) {
     const bool valid = static_cast<unsigned int>(tv) < static_cast<unsigned int>(C);
     bad += (!valid && tv != -1) ? 1u : 0u;
     float xt = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) xt = (c == tv) ? x[c] : xt;
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        x[c] = exp2f((x[c] - m) * kLog2e);
-        s += x[c];
-    }
+    float m, s;
+    int arg;
+    softmax_core<C>(x, m, s, arg);
+    if (s != s) arg = argmax_nan_aware<C>(refetch);
     const float w = valid ? wsm[tv] : 0.f;
-    const float nll = (m - xt) + __logf(s);
+    const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
     step_l += valid ? w * nll : 0.f;
     step_w += w;
     if (do_grad) {
         const float gsc = valid ? w * inv_tw : 0.f;  // exact zeros at ignored pixels even when 1/Σw = inf
-        const float r = __fdividef(gsc, s);
+        const float r = gsc * rcp_ftz(s);
 #pragma unroll
         for (int c = 0; c < C; ++c) x[c] = fmaf(x[c], r, (c == tv) ? -gsc : 0.f);
     }

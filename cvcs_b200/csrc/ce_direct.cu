@@ -35,13 +35,25 @@ __global__ void __launch_bounds__(kThreads, MINB) ce_nchw_kernel(const CeParams 
     double lsum = 0.0, wsum = 0.0;
     unsigned int bad = 0, since_flush = 0;
 
+    // (b, g) = (image, VEC-pixel group inside the image) of this thread's item, advanced incrementally:
+    // one integer division per kernel instead of one per item
+    const unsigned int ipi = p.items_per_image;
+    const unsigned int stride = gridDim.x * kThreads;
+    const unsigned int step_b = stride / ipi, step_g = stride - step_b * ipi;
+    unsigned int b, g;
+    {
+        const unsigned int first = blockIdx.x * kThreads + threadIdx.x;
+        b = first / ipi;
+        g = first - b * ipi;
+    }
     for (long long base = static_cast<long long>(blockIdx.x) * kThreads; base < p.n_items;
-         base += static_cast<long long>(gridDim.x) * kThreads) {
+         base += stride, b += step_b, g += step_g) {
+        if (g >= ipi) {
+            g -= ipi;
+            ++b;
+        }
         const long long item = base + threadIdx.x;
         if (item < p.n_items) {
-            const unsigned int item32 = static_cast<unsigned int>(item);  // n_items < 2^31 (host-checked)
-            const unsigned int b = item32 / p.items_per_image;
-            const unsigned int g = item32 - b * p.items_per_image;
             const long long pix = static_cast<long long>(b) * p.hw + static_cast<long long>(g) * VEC;
             const long long off0 = static_cast<long long>(b) * C * p.hw + static_cast<long long>(g) * VEC;
 
@@ -60,7 +72,11 @@ __global__ void __launch_bounds__(kThreads, MINB) ce_nchw_kernel(const CeParams 
             float step_l = 0.f, step_w = 0.f;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                amax[k] = pixel_ce<C>(x[k], t[k], wsm, inv_tw, do_grad, step_l, step_w, bad);
+                amax[k] = pixel_ce<C>(x[k], t[k], wsm, inv_tw, do_grad, step_l, step_w, bad, [&](int c) {
+                    float v[1];  // rows with NaN / inf only: one scalar re-read per class
+                    VecIO<T, 1>::load(logits + off0 + c * p.hw + k, v);
+                    return v[0];
+                });
                 if (do_conf && static_cast<unsigned int>(t[k]) < static_cast<unsigned int>(C)) conf.add(t[k] * C + amax[k]);
             }
             lsum += static_cast<double>(step_l);
@@ -138,19 +154,19 @@ __global__ void __launch_bounds__(kThreads) ce_generic_kernel(const CeParams p, 
             float xc[1];
             VecIO<T, 1>::load(logits + off0 + c * class_stride, xc);
             xt = (c == tv) ? xc[0] : xt;
-            s += exp2f((xc[0] - m) * kLog2e);
+            s += ex2_ftz((xc[0] - m) * kLog2e);
         }
         const float w = valid ? wsm[tv] : 0.f;
-        const float nll = (m - xt) + __logf(s);
+        const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
         lsum += valid ? static_cast<double>(w * nll) : 0.0;
         wsum += static_cast<double>(w);
         if (do_grad) {
             const float gsc = valid ? w * inv_tw : 0.f;
-            const float r = __fdividef(gsc, s);
+            const float r = gsc * rcp_ftz(s);
             for (int c = 0; c < C; ++c) {
                 float xc[1];
                 VecIO<T, 1>::load(logits + off0 + c * class_stride, xc);
-                xc[0] = fmaf(exp2f((xc[0] - m) * kLog2e), r, (c == tv) ? -gsc : 0.f);
+                xc[0] = fmaf(ex2_ftz((xc[0] - m) * kLog2e), r, (c == tv) ? -gsc : 0.f);
                 VecIO<T, 1>::store(dlogits + off0 + c * class_stride, xc);
             }
         }

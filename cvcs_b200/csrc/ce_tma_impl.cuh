@@ -47,16 +47,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    // try_wait suspends the thread in hardware until the phase completes or the time hint (ns)
+    // expires; the large hint keeps waiting warps out of the issue slots the working warps need
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"(0x989680)
         : "memory");
 }
 // global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
@@ -78,6 +80,8 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- chunk addressing -----------------------------------------------------------------------
+// A CTA walks chunks q = blockIdx.x, blockIdx.x + gridDim.x, ...  For NCHW a chunk is P pixels of
+// one image (b, k); the walker advances (b, k) incrementally so the loops hold no integer division.
 struct Chunk {
     long long pix0;    // global pixel index of the chunk's first pixel (b*hw + k*P for NCHW)
     long long elem0;   // NCHW: element offset of plane 0 (b*C*hw + k*P); NHWC: pix0 * C
@@ -85,24 +89,69 @@ struct Chunk {
 };
 
 template <int C, int P, bool NHWC>
-__device__ __forceinline__ Chunk chunk_of(const CeParams& p, long long q) {
-    Chunk ck;
-    if constexpr (NHWC) {
-        ck.pix0 = q * P;
-        ck.elem0 = ck.pix0 * C;
-        const long long rem = p.n_pixels - ck.pix0;
-        ck.n = rem < P ? static_cast<int>(rem) : P;
-    } else {
-        const unsigned int q32 = static_cast<unsigned int>(q);
-        const unsigned int b = q32 / p.items_per_image;
-        const unsigned int k = q32 - b * p.items_per_image;
-        const long long in_img = static_cast<long long>(k) * P;
-        ck.pix0 = static_cast<long long>(b) * p.hw + in_img;
-        ck.elem0 = static_cast<long long>(b) * C * p.hw + in_img;
-        const long long rem = p.hw - in_img;
-        ck.n = rem < P ? static_cast<int>(rem) : P;
+struct ChunkWalker {
+    unsigned int b, k, step_b, step_k, ipi;
+    long long q;
+    __device__ __forceinline__ void init(const CeParams& p) {
+        q = blockIdx.x;
+        if constexpr (!NHWC) {
+            ipi = p.items_per_image;
+            b = blockIdx.x / ipi;
+            k = blockIdx.x - b * ipi;
+            step_b = gridDim.x / ipi;
+            step_k = gridDim.x - step_b * ipi;
+        }
     }
-    return ck;
+    __device__ __forceinline__ Chunk get(const CeParams& p) const {
+        Chunk ck;
+        if constexpr (NHWC) {
+            ck.pix0 = q * P;
+            ck.elem0 = ck.pix0 * C;
+            const long long rem = p.n_pixels - ck.pix0;
+            ck.n = rem < P ? static_cast<int>(rem) : P;
+        } else {
+            const long long in_img = static_cast<long long>(k) * P;
+            ck.pix0 = static_cast<long long>(b) * p.hw + in_img;
+            ck.elem0 = static_cast<long long>(b) * C * p.hw + in_img;
+            const long long rem = p.hw - in_img;
+            ck.n = rem < P ? static_cast<int>(rem) : P;
+        }
+        return ck;
+    }
+    __device__ __forceinline__ void next() {
+        q += gridDim.x;
+        if constexpr (!NHWC) {
+            k += step_k;
+            b += step_b;
+            if (k >= ipi) {
+                k -= ipi;
+                ++b;
+            }
+        }
+    }
+};
+
+// ring position: stage index + phase parity, advanced without a modulo
+struct Ring {
+    int s;
+    uint32_t phase;
+    __device__ __forceinline__ void next(int S) {
+        if (++s == S) {
+            s = 0;
+            phase ^= 1u;
+        }
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ float lds_elem(const unsigned char* base, int idx) {
+    if constexpr (sizeof(T) == 4) return *reinterpret_cast<const float*>(base + 4 * idx);
+    else return __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(base + 2 * idx)) << 16);
+}
+template <typename T>
+__device__ __forceinline__ void sts_elem(unsigned char* base, int idx, float v) {
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<float*>(base + 4 * idx) = v;
+    else *reinterpret_cast<unsigned short*>(base + 2 * idx) = static_cast<unsigned short>(pack_bf16(v, 0.f) & 0xffffu);
 }
 
 template <typename T, int C, int VECP, bool NHWC, bool PRIV>
@@ -145,9 +194,7 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
             const T* __restrict__ logits = reinterpret_cast<const T*>(p.logits);
             T* __restrict__ dlogits = reinterpret_cast<T*>(p.dlogits);
             const unsigned char* __restrict__ target = reinterpret_cast<const unsigned char*>(p.target);
-            auto issue_load = [&](long long i) {
-                const int s = static_cast<int>(i % S);
-                const Chunk ck = chunk_of<C, P, NHWC>(p, blockIdx.x + i * gridDim.x);
+            auto issue_load = [&](const Chunk& ck, int s) {
                 const uint32_t dst = stage0 + s * g.stage_bytes;
                 const uint32_t bar = bar0 + 8 * s;
                 const uint32_t lbytes = static_cast<uint32_t>(ck.n) * tsize;
@@ -161,9 +208,7 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                 }
                 bulk_g2s(dst + g.label_off, target + ck.pix0 * tsize, lbytes, bar);
             };
-            auto issue_store = [&](long long i) {
-                const int s = static_cast<int>(i % S);
-                const Chunk ck = chunk_of<C, P, NHWC>(p, blockIdx.x + i * gridDim.x);
+            auto issue_store = [&](const Chunk& ck, int s) {
                 const uint32_t src = stage0 + s * g.stage_bytes;
                 if constexpr (NHWC) {
                     bulk_s2g(dlogits + ck.elem0, src, static_cast<uint32_t>(ck.n) * C * ES);
@@ -174,21 +219,38 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                 }
                 bulk_commit();
             };
+            // `ld` runs ahead of `st` by up to S chunks
+            ChunkWalker<C, P, NHWC> ld, st;
+            ld.init(p);
+            st.init(p);
+            Ring ld_ring{0, 0u}, st_ring{0, 0u};
+            long long loaded = 0;
             const long long pre = mine < S ? mine : S;
-            for (long long i = 0; i < pre; ++i) issue_load(i);
+            for (; loaded < pre; ++loaded) {
+                issue_load(ld.get(p), ld_ring.s);
+                ld.next();
+                ld_ring.next(S);
+            }
             for (long long i = 0; i < mine; ++i) {
-                const int s = static_cast<int>(i % S);
-                mbar_wait(bar0 + 8 * (kMaxStages + s), static_cast<uint32_t>((i / S) & 1));
+                mbar_wait(bar0 + 8 * (kMaxStages + st_ring.s), st_ring.phase);
                 if (do_grad) {
-                    issue_store(i);
+                    issue_store(st.get(p), st_ring.s);
                     // the stage consumed one step earlier is free once its store has left smem
-                    if (i >= 1 && i - 1 + S < mine) {
+                    if (i >= 1 && loaded < mine) {
                         bulk_wait_read<1>();
-                        issue_load(i - 1 + S);
+                        issue_load(ld.get(p), ld_ring.s);
+                        ld.next();
+                        ld_ring.next(S);
+                        ++loaded;
                     }
-                } else if (i + S < mine) {
-                    issue_load(i + S);
+                } else if (loaded < mine) {
+                    issue_load(ld.get(p), ld_ring.s);
+                    ld.next();
+                    ld_ring.next(S);
+                    ++loaded;
                 }
+                st.next();
+                st_ring.next(S);
             }
             if (do_grad) bulk_wait_all();
         }
@@ -197,136 +259,148 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
         BinAcc<PRIV, kConsumerBar> conf;
         if (do_conf) conf.init(smem + g.hist_off, C * C);
         const float inv_tw = do_grad ? static_cast<float>(p.inv_tw_dev ? *p.inv_tw_dev : p.inv_tw) : 0.f;
+        const int ign8 = ignore_as_int_u8(p.ignore_index);
         unsigned int since_flush = 0;
+        ChunkWalker<C, P, NHWC> walk;
+        walk.init(p);
+        Ring ring{0, 0u};
+        const int pix_t0 = tid * VECP;  // this thread's first pixel inside a chunk
 
         for (long long i = 0; i < mine; ++i) {
-            const int s = static_cast<int>(i % S);
-            const Chunk ck = chunk_of<C, P, NHWC>(p, blockIdx.x + i * gridDim.x);
-            unsigned char* stage = smem + g.stage_off + s * g.stage_bytes;
-            mbar_wait(bar0 + 8 * s, static_cast<uint32_t>((i / S) & 1));
-            if (tid * VECP < ck.n) {
-                float x[VECP][C];
-                // ---- shared -> registers
+            const Chunk ck = walk.get(p);
+            unsigned char* stage = smem + g.stage_off + ring.s * g.stage_bytes;
+            mbar_wait(bar0 + 8 * ring.s, ring.phase);
+            if (pix_t0 < ck.n) {
+                // element index of (class c, pixel j of the chunk) inside the stage
+                auto eidx = [&](int c, int j) { return NHWC ? j * C + c : c * P + j; };
+                // ---- shared -> registers: the thread's VECP pixels x C classes, kept RAW (logit
+                // dtype) so that bf16 holds two values per register; converted pixel by pixel
+                constexpr int WPP = NHWC ? 1 : VECP * ES / 4;                 // words per plane row (NCHW)
+                constexpr int NW = NHWC ? VECP * C * ES / 4 : C * (WPP > 0 ? WPP : 1);
+                static_assert(NHWC ? (VECP * C * ES) % 16 == 0 : (VECP * ES) % 4 == 0, "thread span must be whole words");
+                uint32_t raw[NW];
                 if constexpr (NHWC) {
-                    constexpr int EPV = 16 / ES;  // elements per 16-byte vector
-                    static_assert((VECP * C) % EPV == 0, "NHWC run must be whole 16-byte vectors");
-                    const uint4* src = reinterpret_cast<const uint4*>(stage + static_cast<size_t>(tid) * VECP * C * ES);
+                    const uint4* src = reinterpret_cast<const uint4*>(stage + static_cast<size_t>(pix_t0) * C * ES);
 #pragma unroll
-                    for (int j = 0; j < VECP * C / EPV; ++j) {
+                    for (int j = 0; j < NW / 4; ++j) {
                         const uint4 v = src[j];
-                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int e = 0; e < EPV; ++e) {
-                            const int idx = j * EPV + e;
-                            float f;
-                            if constexpr (ES == 4) f = __uint_as_float(w[e]);
-                            else f = (e & 1) ? bf16_hi(w[e / 2]) : bf16_lo(w[e / 2]);
-                            x[idx / C][idx % C] = f;
-                        }
+                        raw[4 * j] = v.x; raw[4 * j + 1] = v.y; raw[4 * j + 2] = v.z; raw[4 * j + 3] = v.w;
                     }
                 } else {
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const unsigned char* src = stage + (static_cast<size_t>(c) * P + tid * VECP) * ES;
-                        constexpr int BYTES = VECP * ES;
-                        uint32_t w[BYTES >= 4 ? BYTES / 4 : 1];
-                        if constexpr (BYTES == 16) {
+                        const unsigned char* src = stage + (static_cast<size_t>(c) * P + pix_t0) * ES;
+                        if constexpr (WPP == 4) {
                             const uint4 v = *reinterpret_cast<const uint4*>(src);
-                            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-                        } else if constexpr (BYTES == 8) {
+                            raw[4 * c] = v.x; raw[4 * c + 1] = v.y; raw[4 * c + 2] = v.z; raw[4 * c + 3] = v.w;
+                        } else if constexpr (WPP == 2) {
                             const uint2 v = *reinterpret_cast<const uint2*>(src);
-                            w[0] = v.x; w[1] = v.y;
-                        } else if constexpr (BYTES == 4) {
-                            w[0] = *reinterpret_cast<const uint32_t*>(src);
+                            raw[2 * c] = v.x; raw[2 * c + 1] = v.y;
                         } else {
-                            w[0] = *reinterpret_cast<const unsigned short*>(src);
-                        }
-#pragma unroll
-                        for (int k = 0; k < VECP; ++k) {
-                            if constexpr (ES == 4) x[k][c] = __uint_as_float(w[k]);
-                            else x[k][c] = (k & 1) ? bf16_hi(w[k / 2]) : bf16_lo(w[k / 2]);
+                            raw[c] = *reinterpret_cast<const uint32_t*>(src);
                         }
                     }
                 }
+                // flat element number of (class c, thread-local pixel k) inside raw[] (in elements of T)
+                auto ridx = [&](int c, int k) { return NHWC ? k * C + c : c * VECP + k; };
+                auto raw_get = [&](int e) -> float {
+                    if constexpr (ES == 4) return __uint_as_float(raw[e]);
+                    else return (e & 1) ? bf16_hi(raw[e >> 1]) : bf16_lo(raw[e >> 1]);
+                };
                 // ---- labels
                 int t[VECP];
                 const unsigned char* lab = stage + g.label_off;
                 if (p.target_i64) {
 #pragma unroll
                     for (int k = 0; k < VECP; ++k) {
-                        const uint2 v = *reinterpret_cast<const uint2*>(lab + (static_cast<size_t>(tid) * VECP + k) * 8);
+                        const uint2 v = *reinterpret_cast<const uint2*>(lab + (static_cast<size_t>(pix_t0) + k) * 8);
                         t[k] = decode_label_i64(v.x, v.y, p.ignore_index);
                     }
                 } else {
                     uint32_t w[VECP >= 4 ? VECP / 4 : 1];
                     if constexpr (VECP == 8) {
-                        const uint2 v = *reinterpret_cast<const uint2*>(lab + tid * 8);
+                        const uint2 v = *reinterpret_cast<const uint2*>(lab + pix_t0);
                         w[0] = v.x; w[1] = v.y;
                     } else if constexpr (VECP == 4) {
-                        w[0] = *reinterpret_cast<const uint32_t*>(lab + tid * 4);
+                        w[0] = *reinterpret_cast<const uint32_t*>(lab + pix_t0);
                     } else if constexpr (VECP == 2) {
-                        w[0] = *reinterpret_cast<const unsigned short*>(lab + tid * 2);
+                        w[0] = *reinterpret_cast<const unsigned short*>(lab + pix_t0);
                     } else {
-                        w[0] = lab[tid];
+                        w[0] = lab[pix_t0];
                     }
-                    decode_labels_u8<VECP>(w, p.ignore_index, t);
+#pragma unroll
+                    for (int k = 0; k < VECP; ++k) {
+                        const int v = (w[k / 4] >> (8 * (k % 4))) & 0xff;
+                        t[k] = (v == ign8) ? -1 : v;
+                    }
                 }
-                // ---- math
+                // ---- math, one pixel at a time (the compiler interleaves the unrolled pixels)
                 int amax[VECP];
+                float gfix[VECP];     // gradient of the target class, patched into the stage afterwards
                 float step_l = 0.f, step_w = 0.f;
 #pragma unroll
                 for (int k = 0; k < VECP; ++k) {
-                    amax[k] = pixel_ce<C>(x[k], t[k], wsm, inv_tw, do_grad, step_l, step_w, bad);
-                    if (do_conf && static_cast<unsigned int>(t[k]) < static_cast<unsigned int>(C)) conf.add(t[k] * C + amax[k]);
-                }
-                lsum += static_cast<double>(step_l);
-                wsum += static_cast<double>(step_w);
-                // ---- registers -> shared (in place)
-                if (do_grad) {
-                    if constexpr (NHWC) {
-                        constexpr int EPV = 16 / ES;
-                        uint4* dst = reinterpret_cast<uint4*>(stage + static_cast<size_t>(tid) * VECP * C * ES);
+                    const int tv = t[k];
+                    const bool valid = static_cast<unsigned int>(tv) < static_cast<unsigned int>(C);
+                    bad += (!valid && tv != -1) ? 1u : 0u;
+                    const int tc = valid ? tv : 0;
+                    // the target logit and its class weight by dynamic index from shared memory
+                    const float xt = lds_elem<T>(stage, eidx(tc, pix_t0 + k));
+                    const float w = valid ? wsm[tc] : 0.f;
+                    float x[C];
 #pragma unroll
-                        for (int j = 0; j < VECP * C / EPV; ++j) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                if constexpr (ES == 4) {
-                                    const int idx = j * 4 + e;
-                                    w[e] = __float_as_uint(x[idx / C][idx % C]);
-                                } else {
-                                    const int i0 = j * 8 + 2 * e, i1 = i0 + 1;
-                                    w[e] = pack_bf16(x[i0 / C][i0 % C], x[i1 / C][i1 % C]);
-                                }
-                            }
-                            dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                    } else {
+                    for (int c = 0; c < C; ++c) x[c] = raw_get(ridx(c, k));
+                    float m, s;
+                    int arg;
+                    softmax_core<C>(x, m, s, arg);
+                    if (s != s) arg = argmax_nan_aware<C>([&](int c) { return lds_elem<T>(stage, eidx(c, pix_t0 + k)); });
+                    amax[k] = arg;
+                    const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
+                    step_l += valid ? w * nll : 0.f;
+                    step_w += w;
+                    if (do_conf && valid) conf.add(tv * C + arg);
+                    if (do_grad) {
+                        const float gsc = valid ? w * inv_tw : 0.f;  // exact zeros at ignored pixels
+                        const float r = gsc * rcp_ftz(s);
+                        gfix[k] = fmaf(ex2_ftz((xt - m) * kLog2e), r, -gsc);
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
-                            unsigned char* dst = stage + (static_cast<size_t>(c) * P + tid * VECP) * ES;
-                            constexpr int BYTES = VECP * ES;
-                            uint32_t w[BYTES >= 4 ? BYTES / 4 : 1];
+                            const float gv = x[c] * r;
+                            const int e = ridx(c, k);
                             if constexpr (ES == 4) {
-#pragma unroll
-                                for (int k = 0; k < VECP; ++k) w[k] = __float_as_uint(x[k][c]);
-                            } else if constexpr (VECP >= 2) {
-#pragma unroll
-                                for (int k = 0; k < VECP / 2; ++k) w[k] = pack_bf16(x[2 * k][c], x[2 * k + 1][c]);
-                            } else {
-                                w[0] = pack_bf16(x[0][c], 0.f);
+                                raw[e] = __float_as_uint(gv);
+                            } else {  // bf16: RNE, merged into the half of the word this pixel owns
+                                const uint32_t h = pack_bf16(gv, 0.f) & 0xffffu;
+                                raw[e >> 1] = (e & 1) ? ((raw[e >> 1] & 0x0000ffffu) | (h << 16)) : ((raw[e >> 1] & 0xffff0000u) | h);
                             }
-                            if constexpr (BYTES == 16) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-                            else if constexpr (BYTES == 8) *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
-                            else if constexpr (BYTES == 4) *reinterpret_cast<uint32_t*>(dst) = w[0];
-                            else *reinterpret_cast<unsigned short*>(dst) = static_cast<unsigned short>(w[0]);
                         }
                     }
                 }
-                if (do_arg) store_argmax<VECP>(p, ck.pix0 + tid * VECP, amax);
+                lsum += static_cast<double>(step_l);
+                wsum += static_cast<double>(step_w);
+                // ---- registers -> shared (in place), then the target-class entries
+                if (do_grad) {
+                    if constexpr (NHWC) {
+                        uint4* dst = reinterpret_cast<uint4*>(stage + static_cast<size_t>(pix_t0) * C * ES);
+#pragma unroll
+                        for (int j = 0; j < NW / 4; ++j) dst[j] = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            unsigned char* dst = stage + (static_cast<size_t>(c) * P + pix_t0) * ES;
+                            if constexpr (WPP == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(raw[4 * c], raw[4 * c + 1], raw[4 * c + 2], raw[4 * c + 3]);
+                            else if constexpr (WPP == 2) *reinterpret_cast<uint2*>(dst) = make_uint2(raw[2 * c], raw[2 * c + 1]);
+                            else *reinterpret_cast<uint32_t*>(dst) = raw[c];
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < VECP; ++k)
+                        if (static_cast<unsigned int>(t[k]) < static_cast<unsigned int>(C)) sts_elem<T>(stage, eidx(t[k], pix_t0 + k), gfix[k]);
+                }
+                if (do_arg) store_argmax<VECP>(p, ck.pix0 + pix_t0, amax);
             }
             if (do_grad) fence_async_smem();  // make the in-place gradients visible to the bulk store
-            mbar_arrive(bar0 + 8 * (kMaxStages + s));
+            mbar_arrive(bar0 + 8 * (kMaxStages + ring.s));
             if (PRIV && do_conf) {
                 since_flush += VECP;
                 if (since_flush > 65535u - VECP) {
@@ -334,6 +408,8 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                     since_flush = 0;
                 }
             }
+            walk.next();
+            ring.next(S);
         }
         if (do_conf) conf.flush(p.confmat);
     }
