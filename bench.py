@@ -42,6 +42,11 @@ WORKLOADS = {
                  desc="same path with bf16 logits, class weights and ignore_index=255 (LoveDA-style labels)"),
     "cfg5": dict(B=16, C=20, H=1024, W=1024, dtype="f32", weighted=False, ignore_index=-100,
                  desc="20-class head, fp32 logits (the cfg5 head at batch 16 per GPU)"),
+    # K5 alone: the tiler / normaliser either side of the model (Cb + Cb*s_out + 2 bytes/px)
+    "tile13": dict(kind="tile", B=64, Cb=13, H=1024, W=1024, dtype="f32", scene=8192,
+                   desc="cfg5 tiler: 13-band u8 scene -> 64 normalised fp32 tiles of 1024x1024 + label tiles"),
+    "tile3": dict(kind="tile", B=64, Cb=3, H=1024, W=1024, dtype="f32", scene=8192,
+                  desc="RGB tiler: u8 scene -> 64 fp32 tiles of 1024x1024 (train.py:121 cast) + label tiles"),
 }
 
 
@@ -200,6 +205,87 @@ def run_reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def run_tile_bench(args, wl):
+    """Secondary workload: K5 (tile gather + cast + normalise + label tiles) on one GPU."""
+    import torch
+    from cvcs_b200 import ops
+    from oracle import torch_path
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, Cb, p, S = wl["B"], wl["Cb"], wl["H"], wl["scene"]
+    g = torch.Generator(device=dev).manual_seed(7)
+    scene = torch.randint(0, 256, (Cb, S, S), generator=g, device=dev, dtype=torch.uint8)
+    label = torch.randint(0, 20, (S // 32, S // 32), generator=g, device=dev, dtype=torch.uint8)
+    label = label.repeat_interleave(32, 0).repeat_interleave(32, 1).contiguous()
+    cols = S // p
+    yx = torch.tensor([((i // cols) * p, (i % cols) * p) for i in range(B)], dtype=torch.int32, device=dev)
+    normalise = Cb != 3
+    mean = (torch.arange(Cb, device=dev, dtype=torch.float32) * 7 + 90) if normalise else None
+    std = (torch.arange(Cb, device=dev, dtype=torch.float32) * 3 + 40) if normalise else None
+    outs = [torch.empty((B, Cb, p, p), dtype=torch.float32, device=dev) for _ in range(2)]
+    labs = [torch.empty((B, p, p), dtype=torch.uint8, device=dev) for _ in range(2)]
+    ev = []
+
+    def step(i, timed):
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        ops.tile_normalize(scene, yx, (p, p), mean, std, out=outs[i % 2], label=label, label_out=labs[i % 2])
+        if timed:
+            e1.record()
+            ev.append((e0, e1))
+
+    for i in range(args.warmup):
+        step(i, False)
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(0)
+    sampler.start()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        step(i, True)
+    end.record()
+    torch.cuda.synchronize(dev)
+    sampler.stop()
+    ms = start.elapsed_time(end) / args.steps
+    k_ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    px = B * p * p
+    bpp = Cb + Cb * 4 + 2
+    peak, peak_src = load_peaks()
+    achieved = bpp * px / (k_ms * 1e-3) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline:
+        hs, hl = scene[:, :2 * p, :2 * p].cpu(), label[:2 * p, :2 * p].cpu()
+        torch.set_num_threads(os.cpu_count() or 1)
+
+        def ref_once():
+            t0 = time.perf_counter()
+            for ty, tx in ((0, 0), (0, p), (p, 0), (p, p)):
+                t = torch_path.crop(hs, ty, tx, p, p)
+                torch_path.crop(hl[None], ty, tx, p, p)
+                t = t.type(torch.float32)
+                if normalise:
+                    t = (t - mean.cpu()[:, None, None]) / std.cpu()[:, None, None]
+            return time.perf_counter() - t0
+        ref_once()
+        sec = min(ref_once() for _ in range(3))
+        cpu = {"value": 4 * p * p / sec / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"4 tiles of {p}x{p}, {Cb} bands per step; best of 3"}
+    line = {
+        "metric": "Gpixel/s tile gather + cast/normalise (K5)", "value": px / (ms * 1e-3) / 1e9, "unit": UNIT,
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8->f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "tiles_per_step": B, "bands": Cb, "tile": [p, p],
+                   "scene": [Cb, S, S], "normalise": normalise,
+                   "l2": f"outputs larger than L2: 2 rotating sets of {px * Cb * 4 / 1e6:.0f} MB"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": load_traffic(args.workload), "kernel": "cvcs K5 tile_normalize", "bytes_per_pixel": bpp,
+                     "pixels_per_launch": px, "avg_launch_ms": k_ms, "peak_source": peak_src},
+        "cpu_baseline": cpu, "e2e": None, "gpu_launches": args.steps, "clocks": sampler.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -210,15 +296,23 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
     ap.add_argument("--path", default="auto", choices=["auto", "tma", "direct", "generic"])
     ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--no-wait-hint", action="store_true", help="A/B: mbarrier waits without the suspend-time hint")
+    ap.add_argument("--bf16-vecp", type=int, default=0, help="A/B: pixels per thread of the bf16 TMA variant (4 or 8)")
     ap.add_argument("--label-dtype", default="u8", choices=["u8", "i64"])
     ap.add_argument("--no-grad", action="store_true", help="forward/eval only (no dlogits)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-copy-ref", action="store_true", help="skip the same-size torch copy reference measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
         wl["B"] = args.batch
+    if wl.get("kind") == "tile":
+        if args.impl == "reference" or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            raise SystemExit("the tile workloads are single-GPU secondary measurements of the b200 arm")
+        run_tile_bench(args, wl)
+        return
     if args.impl == "reference":
         run_reference_arm(args, wl)
         return
@@ -241,6 +335,8 @@ def main():
 
     _lib.set_option(_lib.OPT_CE_PATH, {"auto": 0, "tma": 1, "direct": 2, "generic": 3}[args.path])
     _lib.set_option(_lib.OPT_TMA_STAGES, args.stages)
+    _lib.set_option(_lib.OPT_TMA_WAIT_HINT, 1 if args.no_wait_hint else 0)
+    _lib.set_option(_lib.OPT_TMA_BF16_VECP, args.bf16_vecp)
 
     B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
     esize = 4 if wl["dtype"] == "f32" else 2
@@ -334,6 +430,23 @@ def main():
     gpu_launches = launches["n"]
     total_cm = int(confmat.sum().item())
 
+    # ---- same-size copy, same harness (events around every launch, rotating buffers): what a plain
+    # device-to-device copy of K1's logits -> dlogits bytes reaches here; context for roofline.frac
+    copy_gbs = None
+    if grad and not args.no_copy_ref:
+        cp = []
+        for i in range(10 + 50):
+            x, _ = sets[i % n_sets]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dl[i % n_sets].copy_(x)
+            e1.record()
+            if i >= 10:
+                cp.append((e0, e1))
+        torch.cuda.synchronize(dev)
+        cp_ms = sum(a.elapsed_time(b) for a, b in cp) / len(cp)
+        copy_gbs = 2 * px_per_gpu * C * esize / (cp_ms * 1e-3) / 1e9
+
     # ---- roofline of the dominant kernel (K1) -----------------------------------------------------
     peak, peak_src = load_peaks()
     bpp = algorithmic_bytes_per_pixel(C, esize, grad)
@@ -342,7 +455,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_traffic(args.workload), "kernel": "cvcs K1 ce_fused", "bytes_per_pixel": bpp,
                 "pixels_per_launch": px_per_gpu, "avg_launch_ms": k1_avg_ms, "peak_source": peak_src,
-                "frac_of_8TBps_nominal": achieved / 8000.0}
+                "frac_of_8TBps_nominal": achieved / 8000.0, "same_size_copy_gbs_in_this_harness": copy_gbs}
 
     # ---- e2e through the host-buffer C-ABI call ----------------------------------------------------
     e2e = None

@@ -28,6 +28,7 @@ constexpr int kConsumerBar = 1;  // named barrier of the 256 consumer threads
 
 struct Geom {
     int stages;
+    int wait_hint;     // 1: consumers' and producer's mbarrier waits pass a long suspend-time hint
     int stage_bytes;   // logits + labels, multiple of 128
     int label_off;     // offset of the labels inside a stage
     int hist_off;      // offset of the bin accumulators in dynamic smem
@@ -46,20 +47,35 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+template <bool HINT>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    // try_wait suspends the thread in hardware until the phase completes or the time hint (ns)
-    // expires; the large hint keeps waiting warps out of the issue slots the working warps need
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity), "r"(0x989680)
-        : "memory");
+    // try_wait suspends the thread in hardware until the phase completes or a time limit expires;
+    // HINT passes an explicit (long) limit so that waiting warps stay out of the issue slots
+    if constexpr (HINT) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "LAB_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+            "@P1 bra DONE;\n"
+            "bra LAB_WAIT;\n"
+            "DONE:\n"
+            "}\n" ::"r"(bar),
+            "r"(parity), "r"(0x989680)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "LAB_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+            "@P1 bra DONE;\n"
+            "bra LAB_WAIT;\n"
+            "DONE:\n"
+            "}\n" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+    }
 }
 // global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -154,7 +170,7 @@ __device__ __forceinline__ void sts_elem(unsigned char* base, int idx, float v) 
     else *reinterpret_cast<unsigned short*>(base + 2 * idx) = static_cast<unsigned short>(pack_bf16(v, 0.f) & 0xffffu);
 }
 
-template <typename T, int C, int VECP, bool NHWC, bool PRIV>
+template <typename T, int C, int VECP, bool NHWC, bool PRIV, bool GRAD>
 __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const Geom g) {
     constexpr int P = kThreads * VECP;
     constexpr int ES = sizeof(T);
@@ -163,7 +179,7 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
     __shared__ __align__(8) unsigned long long bars[2 * kMaxStages];  // full[S], done[S]
 
     const int tid = threadIdx.x;
-    const bool do_grad = p.dlogits != nullptr;
+    constexpr bool do_grad = GRAD;
     const bool do_arg = p.argmax != nullptr;
     const bool do_conf = p.confmat != nullptr;
     const int S = g.stages;
@@ -232,7 +248,8 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                 ld_ring.next(S);
             }
             for (long long i = 0; i < mine; ++i) {
-                mbar_wait(bar0 + 8 * (kMaxStages + st_ring.s), st_ring.phase);
+                if (g.wait_hint) mbar_wait<true>(bar0 + 8 * (kMaxStages + st_ring.s), st_ring.phase);
+                else mbar_wait<false>(bar0 + 8 * (kMaxStages + st_ring.s), st_ring.phase);
                 if (do_grad) {
                     issue_store(st.get(p), st_ring.s);
                     // the stage consumed one step earlier is free once its store has left smem
@@ -269,7 +286,8 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
         for (long long i = 0; i < mine; ++i) {
             const Chunk ck = walk.get(p);
             unsigned char* stage = smem + g.stage_off + ring.s * g.stage_bytes;
-            mbar_wait(bar0 + 8 * ring.s, ring.phase);
+            if (g.wait_hint) mbar_wait<true>(bar0 + 8 * ring.s, ring.phase);
+            else mbar_wait<false>(bar0 + 8 * ring.s, ring.phase);
             if (pix_t0 < ck.n) {
                 // element index of (class c, pixel j of the chunk) inside the stage
                 auto eidx = [&](int c, int j) { return NHWC ? j * C + c : c * P + j; };
@@ -338,6 +356,7 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                 int amax[VECP];
                 float gfix[VECP];     // gradient of the target class, patched into the stage afterwards
                 float step_l = 0.f, step_w = 0.f;
+                bool anomalous = false;  // some pixel's Σexp is NaN (NaN / +inf / all -inf logits)
 #pragma unroll
                 for (int k = 0; k < VECP; ++k) {
                     const int tv = t[k];
@@ -353,13 +372,12 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                     float m, s;
                     int arg;
                     softmax_core<C>(x, m, s, arg);
-                    if (s != s) arg = argmax_nan_aware<C>([&](int c) { return lds_elem<T>(stage, eidx(c, pix_t0 + k)); });
+                    anomalous |= (s != s);
                     amax[k] = arg;
                     const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
                     step_l += valid ? w * nll : 0.f;
                     step_w += w;
-                    if (do_conf && valid) conf.add(tv * C + arg);
-                    if (do_grad) {
+                    if constexpr (do_grad) {
                         const float gsc = valid ? w * inv_tw : 0.f;  // exact zeros at ignored pixels
                         const float r = gsc * rcp_ftz(s);
                         gfix[k] = fmaf(ex2_ftz((xt - m) * kLog2e), r, -gsc);
@@ -378,8 +396,20 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                 }
                 lsum += static_cast<double>(step_l);
                 wsum += static_cast<double>(step_w);
+                // rows with NaN / inf (rare): redo the argmax with torch's NaN rule from the original
+                // logits, which are still in the stage
+                if (anomalous) {
+#pragma unroll
+                    for (int k = 0; k < VECP; ++k)
+                        amax[k] = argmax_nan_aware<C>([&](int c) { return lds_elem<T>(stage, eidx(c, pix_t0 + k)); });
+                }
+                if (do_conf) {
+#pragma unroll
+                    for (int k = 0; k < VECP; ++k)
+                        if (static_cast<unsigned int>(t[k]) < static_cast<unsigned int>(C)) conf.add(t[k] * C + amax[k]);
+                }
                 // ---- registers -> shared (in place), then the target-class entries
-                if (do_grad) {
+                if constexpr (do_grad) {
                     if constexpr (NHWC) {
                         uint4* dst = reinterpret_cast<uint4*>(stage + static_cast<size_t>(pix_t0) * C * ES);
 #pragma unroll
@@ -399,7 +429,7 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                 }
                 if (do_arg) store_argmax<VECP>(p, ck.pix0 + pix_t0, amax);
             }
-            if (do_grad) fence_async_smem();  // make the in-place gradients visible to the bulk store
+            if constexpr (do_grad) fence_async_smem();  // make the in-place gradients visible to the bulk store
             mbar_arrive(bar0 + 8 * (kMaxStages + ring.s));
             if (PRIV && do_conf) {
                 since_flush += VECP;
@@ -442,8 +472,9 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
         return CVCS_OK;
     }
     g.stages = stages;
+    g.wait_hint = get_option(CVCS_OPT_TMA_WAIT_HINT) == 1 ? 0 : 1;
     const int smem = g.stage_off + stages * g.stage_bytes;
-    auto kernel = ce_tma_kernel<T, C, VECP, NHWC, PRIV>;
+    auto kernel = p.dlogits ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, true> : ce_tma_kernel<T, C, VECP, NHWC, PRIV, false>;
     int grid = 0;
     int rc = persistent_grid(kernel, kBlock, smem, &grid);
     if (rc) return rc;

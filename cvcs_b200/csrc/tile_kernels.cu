@@ -24,135 +24,134 @@ struct TileParams {
     unsigned long long* hist;  // nullable
     Workspace* ws;
     long long hist_ignore;
-    long long n_items;  // n_tiles * tile_h * groups_per_row
-    int Cb, H, W, tile_h, tile_w, groups_per_row, n_tiles;
+    long long n_rows;     // n_tiles * planes * tile_h  (one "row item" = one tile row of one plane)
+    int Cb, H, W, tile_h, tile_w, n_tiles;
+    int planes;           // Cb (+1 when the label plane is gathered in the same launch)
     int out_dtype;        // CVCS_U8 / F32 / BF16
     int label_out_i64;
     int hist_C;
+    int use_lut;          // per-band 256-entry LUT of (v - mean) / std in shared memory
 };
 
-template <int VEC>
-__device__ __forceinline__ void load_u8_row(const unsigned char* __restrict__ plane, int H, int W, int y, int x0,
-                                            unsigned int (&px)[VEC]) {
-    // zero fill outside the scene (torchvision.transforms.functional.crop semantics)
-    if (y < 0 || y >= H) {
+constexpr int kSpan = 4;                 // pixels per thread per access (one 32-bit u8 load)
+constexpr int kUnroll = 4;               // independent accesses per thread per row item
+constexpr int kRowBlock = 32 * kSpan * kUnroll;  // pixels of a tile row one warp covers per step (512)
+
+// 4 consecutive u8 of a scene row starting at column x0 (zero fill outside the scene, as
+// torchvision.transforms.functional.crop pads); `row` is NULL for rows outside the scene.
+__device__ __forceinline__ uint32_t load_u8x4(const unsigned char* __restrict__ row, int W, int x0) {
+    if (row == nullptr) return 0u;
+    if (x0 >= 0 && x0 + 3 < W && ((reinterpret_cast<uintptr_t>(row + x0) & 3u) == 0))
+        return __ldcs(reinterpret_cast<const unsigned int*>(row + x0));
+    uint32_t w = 0u;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) px[k] = 0u;
-        return;
-    }
-    const unsigned char* row = plane + static_cast<long long>(y) * W;
-    if constexpr (VEC == 4) {
-        if (x0 >= 0 && x0 + 3 < W && ((reinterpret_cast<uintptr_t>(row + x0) & 3u) == 0)) {
-            const unsigned int w = __ldcs(reinterpret_cast<const unsigned int*>(row + x0));
-            px[0] = w & 0xff;
-            px[1] = (w >> 8) & 0xff;
-            px[2] = (w >> 16) & 0xff;
-            px[3] = w >> 24;
-            return;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
+    for (int k = 0; k < 4; ++k) {
         const int x = x0 + k;
-        px[k] = (x >= 0 && x < W) ? row[x] : 0u;
+        if (x >= 0 && x < W) w |= static_cast<uint32_t>(row[x]) << (8 * k);
     }
+    return w;
 }
 
-template <int VEC, bool PRIV>
+// One warp gathers one tile row of one plane per step: lane l handles the 4-pixel groups
+// l, l + 32, l + 64, l + 96 of each 512-pixel block, so every load instruction reads 128
+// contiguous bytes of the scene row and every store instruction writes 512 (fp32) / 256 (bf16) /
+// 128 (u8) contiguous bytes of the tile row, with kUnroll independent accesses in flight per thread.
+template <bool PRIV>
 __global__ void __launch_bounds__(kThreads) tile_kernel(const TileParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned int is_last;
     const bool do_hist = p.hist != nullptr;
+    float* lut = reinterpret_cast<float*>(smem);
+    const int lut_bytes = p.use_lut ? p.Cb * 256 * 4 : 0;
+    if (p.use_lut) {
+        // IEEE sub / div exactly as torch's sub_(mean).div_(std): 256 possible inputs per band
+        for (int i = threadIdx.x; i < p.Cb * 256; i += kThreads) {
+            const int cb = i >> 8;
+            lut[i] = __fdiv_rn(__fsub_rn(static_cast<float>(i & 255), __ldg(p.mean + cb)), __ldg(p.stdv + cb));
+        }
+    }
     BinAcc<PRIV> acc;
-    if (do_hist) acc.init(smem, p.hist_C + 2);
-    unsigned int since_flush = 0;
+    if (do_hist) acc.init(smem + lut_bytes, p.hist_C + 2);  // contains the barrier
+    else __syncthreads();
     const long long plane = static_cast<long long>(p.H) * p.W;
     const long long tile_plane = static_cast<long long>(p.tile_h) * p.tile_w;
     const int ign_outside = (p.hist_ignore >= p.hist_C && p.hist_ignore <= 255) ? static_cast<int>(p.hist_ignore) : -1;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+    const long long n_warps = static_cast<long long>(gridDim.x) * kWarps;
 
-    for (long long base = static_cast<long long>(blockIdx.x) * kThreads; base < p.n_items;
-         base += static_cast<long long>(gridDim.x) * kThreads) {
-        const long long item = base + threadIdx.x;
-        if (item < p.n_items) {
-            const unsigned int it = static_cast<unsigned int>(item);
-            const unsigned int rowi = it / p.groups_per_row;       // tile * tile_h + y
-            const int xg = static_cast<int>(it - rowi * p.groups_per_row);
-            const unsigned int tile = rowi / p.tile_h;
-            const int y = static_cast<int>(rowi - tile * p.tile_h);
-            const int sy = __ldg(p.tile_yx + 2 * tile) + y;
-            const int sx = __ldg(p.tile_yx + 2 * tile + 1) + xg * VEC;
-            const long long opix = static_cast<long long>(y) * p.tile_w + xg * VEC;  // inside a tile plane
-            const long long slot = p.tile_slot ? __ldg(p.tile_slot + tile) : static_cast<long long>(tile);
+    for (long long item = warp0; item < p.n_rows; item += n_warps) {
+        // item -> (tile, plane, y): plane-major inside a tile so that a warp's consecutive items
+        // walk down the rows of one plane
+        const unsigned int it = static_cast<unsigned int>(item);
+        const unsigned int tp = it / p.tile_h;
+        const int y = static_cast<int>(it - tp * p.tile_h);
+        const unsigned int tile = tp / p.planes;
+        const int pl = static_cast<int>(tp - tile * p.planes);
+        const bool is_label = pl == p.Cb;
+        const int sy = __ldg(p.tile_yx + 2 * tile) + y;
+        const int sx0 = __ldg(p.tile_yx + 2 * tile + 1);
+        const long long slot = p.tile_slot ? __ldg(p.tile_slot + tile) : static_cast<long long>(tile);
+        const unsigned char* src_plane = is_label ? p.label : p.scene + pl * plane;
+        const unsigned char* row = (sy >= 0 && sy < p.H) ? src_plane + static_cast<long long>(sy) * p.W : nullptr;
+        const long long obase = (is_label ? slot : slot * p.Cb + pl) * tile_plane + static_cast<long long>(y) * p.tile_w;
 
-            for (int cb = 0; cb < p.Cb; ++cb) {
-                unsigned int px[VEC];
-                load_u8_row<VEC>(p.scene + cb * plane, p.H, p.W, sy, sx, px);
-                const long long o = (slot * p.Cb + cb) * tile_plane + opix;
-                if (p.out_dtype == CVCS_U8) {
-                    unsigned char* out = reinterpret_cast<unsigned char*>(p.out) + o;
-                    if constexpr (VEC == 4) {
-                        __stcs(reinterpret_cast<unsigned int*>(out), px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24));
-                    } else {
-                        out[0] = static_cast<unsigned char>(px[0]);
-                    }
-                } else {
-                    float f[VEC];
-                    if (p.mean) {
-                        const float m = __ldg(p.mean + cb), s = __ldg(p.stdv + cb);
+        for (int xb = 0; xb < p.tile_w; xb += kRowBlock) {
+            uint32_t w[kUnroll];
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k)
-                            f[k] = __fdiv_rn(__fsub_rn(static_cast<float>(px[k]), m), s);  // IEEE, as sub_().div_()
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) f[k] = static_cast<float>(px[k]);
-                    }
-                    if (p.out_dtype == CVCS_F32) VecIO<float, VEC>::store(reinterpret_cast<float*>(p.out) + o, f);
-                    else VecIO<__nv_bfloat16, VEC>::store(reinterpret_cast<__nv_bfloat16*>(p.out) + o, f);
-                }
+            for (int u = 0; u < kUnroll; ++u) {
+                const int x = xb + (u * 32 + lane) * kSpan;
+                w[u] = (x < p.tile_w) ? load_u8x4(row, p.W, sx0 + x) : 0u;
             }
-            if (p.label) {
-                unsigned int lb[VEC];
-                load_u8_row<VEC>(p.label, p.H, p.W, sy, sx, lb);
-                const long long o = slot * tile_plane + opix;
-                if (p.label_out) {
-                    if (p.label_out_i64) {
-                        long long* out = reinterpret_cast<long long*>(p.label_out) + o;
-                        if constexpr (VEC == 4) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int x = xb + (u * 32 + lane) * kSpan;
+                if (x >= p.tile_w) continue;
+                const long long o = obase + x;
+                if (is_label) {
+                    if (p.label_out) {
+                        if (p.label_out_i64) {
+                            long long* out = reinterpret_cast<long long*>(p.label_out) + o;
                             Raw<16> r;
-                            r.v = make_uint4(lb[0], 0u, lb[1], 0u);
+                            r.v = make_uint4(w[u] & 0xff, 0u, (w[u] >> 8) & 0xff, 0u);
                             r.store(out);
-                            r.v = make_uint4(lb[2], 0u, lb[3], 0u);
+                            r.v = make_uint4((w[u] >> 16) & 0xff, 0u, w[u] >> 24, 0u);
                             r.store(out + 2);
                         } else {
-                            out[0] = lb[0];
-                        }
-                    } else {
-                        unsigned char* out = reinterpret_cast<unsigned char*>(p.label_out) + o;
-                        if constexpr (VEC == 4) {
-                            __stcs(reinterpret_cast<unsigned int*>(out), lb[0] | (lb[1] << 8) | (lb[2] << 16) | (lb[3] << 24));
-                        } else {
-                            out[0] = static_cast<unsigned char>(lb[0]);
+                            __stcs(reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(p.label_out) + o), w[u]);
                         }
                     }
-                }
-                if (do_hist) {
+                    if (do_hist) {
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) {
-                        const int t = static_cast<int>(lb[k]);
-                        acc.add(t < p.hist_C ? t : (t == ign_outside ? p.hist_C : p.hist_C + 1));
+                        for (int k = 0; k < 4; ++k) {
+                            const int t = static_cast<int>((w[u] >> (8 * k)) & 0xff);
+                            acc.add(t < p.hist_C ? t : (t == ign_outside ? p.hist_C : p.hist_C + 1));
+                        }
                     }
+                } else if (p.out_dtype == CVCS_U8) {
+                    __stcs(reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(p.out) + o), w[u]);
+                } else {
+                    float f[4];
+                    if (p.use_lut) {
+                        const float* l = lut + (pl << 8);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) f[k] = l[(w[u] >> (8 * k)) & 0xff];
+                    } else if (p.mean) {
+                        const float m = __ldg(p.mean + pl), s = __ldg(p.stdv + pl);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) f[k] = __fdiv_rn(__fsub_rn(static_cast<float>((w[u] >> (8 * k)) & 0xff), m), s);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) f[k] = static_cast<float>((w[u] >> (8 * k)) & 0xff);
+                    }
+                    if (p.out_dtype == CVCS_F32) VecIO<float, 4>::store(reinterpret_cast<float*>(p.out) + o, f);
+                    else VecIO<__nv_bfloat16, 4>::store(reinterpret_cast<__nv_bfloat16*>(p.out) + o, f);
                 }
-            }
-        }
-        if (PRIV && do_hist) {
-            since_flush += VEC;
-            if (since_flush > 65535u - VEC) {
-                acc.flush(p.ws->hist);
-                since_flush = 0;
             }
         }
     }
     if (!do_hist) return;
+    // PRIV counters are u16: the launcher bounds the label pixels per lane so they cannot overflow
     acc.flush(p.ws->hist);
     if (threadIdx.x == 0) {
         __threadfence();
@@ -170,6 +169,47 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const TileParams p) {
     if (threadIdx.x == 0) {
         p.ws->ticket = 0u;
         __threadfence();
+    }
+}
+
+// Scalar variant for tile widths that are not a multiple of 4 (or unaligned output pointers): one
+// pixel per thread, same item order.
+__global__ void __launch_bounds__(kThreads) tile_kernel_scalar(const TileParams p) {
+    const long long plane = static_cast<long long>(p.H) * p.W;
+    const long long tile_plane = static_cast<long long>(p.tile_h) * p.tile_w;
+    const long long total = p.n_rows * p.tile_w;
+    const int ign_outside = (p.hist_ignore >= p.hist_C && p.hist_ignore <= 255) ? static_cast<int>(p.hist_ignore) : -1;
+    for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * kThreads) {
+        const long long item = i / p.tile_w;
+        const int x = static_cast<int>(i - item * p.tile_w);
+        const long long tp = item / p.tile_h;
+        const int y = static_cast<int>(item - tp * p.tile_h);
+        const long long tile = tp / p.planes;
+        const int pl = static_cast<int>(tp - tile * p.planes);
+        const bool is_label = pl == p.Cb;
+        const int sy = p.tile_yx[2 * tile] + y, sx = p.tile_yx[2 * tile + 1] + x;
+        const long long slot = p.tile_slot ? p.tile_slot[tile] : tile;
+        const unsigned char* src_plane = is_label ? p.label : p.scene + pl * plane;
+        const unsigned int v = (sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) ? src_plane[static_cast<long long>(sy) * p.W + sx] : 0u;
+        const long long o = (is_label ? slot : slot * p.Cb + pl) * tile_plane + static_cast<long long>(y) * p.tile_w + x;
+        if (is_label) {
+            if (p.label_out) {
+                if (p.label_out_i64) reinterpret_cast<long long*>(p.label_out)[o] = v;
+                else reinterpret_cast<unsigned char*>(p.label_out)[o] = static_cast<unsigned char>(v);
+            }
+            if (p.hist) {
+                const int t = static_cast<int>(v);
+                atomicAdd(p.hist + (t < p.hist_C ? t : (t == ign_outside ? p.hist_C : p.hist_C + 1)), 1ull);
+            }
+        } else if (p.out_dtype == CVCS_U8) {
+            reinterpret_cast<unsigned char*>(p.out)[o] = static_cast<unsigned char>(v);
+        } else {
+            float f = static_cast<float>(v);
+            if (p.mean) f = __fdiv_rn(__fsub_rn(f, p.mean[pl]), p.stdv[pl]);
+            if (p.out_dtype == CVCS_F32) reinterpret_cast<float*>(p.out)[o] = f;
+            else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(f);
+        }
     }
 }
 
@@ -283,27 +323,45 @@ int tile_launch(const unsigned char* scene, int Cb, int H, int W, const int* til
     p.tile_h = tile_h;
     p.tile_w = tile_w;
     p.n_tiles = n_tiles;
+    p.planes = Cb + ((label && (label_out || hist)) ? 1 : 0);
+    p.n_rows = static_cast<long long>(n_tiles) * p.planes * tile_h;
     p.out_dtype = out_dtype;
     p.label_out_i64 = label_out_dtype == CVCS_I64;
     p.hist_C = hist_C;
-    const int vec = vec4 ? 4 : 1;
-    p.groups_per_row = tile_w / vec;
-    p.n_items = rows * p.groups_per_row;
-    CVCS_REQUIRE(p.n_items < (1ll << 32), "cvcs_tile_normalize: too many work items");
-    const bool priv = !hist || hist_C + 2 <= 64;
-    const int smem = hist ? (priv ? BinAcc<true>::smem_bytes(hist_C + 2) : BinAcc<false>::smem_bytes(hist_C + 2)) : 0;
-    const long long blocks = (p.n_items + kThreads - 1) / kThreads;
-    long long g = static_cast<long long>(num_sms()) * (smem > 24 * 1024 ? 4 : 8);
-    if (g > blocks) g = blocks;
-    if (g > kMaxGrid) g = kMaxGrid;
-    const int grid = static_cast<int>(g);
-    if (vec4) {
-        if (priv) tile_kernel<4, true><<<grid, kThreads, smem, stream>>>(p);
-        else tile_kernel<4, false><<<grid, kThreads, smem, stream>>>(p);
-    } else {
-        if (priv) tile_kernel<1, true><<<grid, kThreads, smem, stream>>>(p);
-        else tile_kernel<1, false><<<grid, kThreads, smem, stream>>>(p);
+    p.use_lut = (mean != nullptr && Cb <= 32) ? 1 : 0;
+    CVCS_REQUIRE(p.n_rows < (1ll << 32), "cvcs_tile_normalize: too many work items");
+    if (!vec4) {
+        const long long total = p.n_rows * tile_w;
+        long long g = (total + kThreads - 1) / kThreads;
+        const long long cap = static_cast<long long>(num_sms()) * 8;
+        if (g > cap) g = cap;
+        tile_kernel_scalar<<<static_cast<int>(g < 1 ? 1 : g), kThreads, 0, stream>>>(p);
+        CVCS_CUDA_OK(cudaGetLastError());
+        return CVCS_OK;
     }
+    const bool want_priv = !hist || hist_C + 2 <= 64;
+    const int lut_bytes = p.use_lut ? Cb * 256 * 4 : 0;
+    // grid: as many CTAs as stay resident; with private u16 histogram counters a warp must not
+    // see more than 65535 label pixels per lane, which bounds the row items per warp
+    long long g = static_cast<long long>(num_sms()) * ((lut_bytes + (hist ? 16 * 1024 : 0)) > 24 * 1024 ? 4 : 8);
+    const long long warps_needed = p.n_rows;
+    if (g * kWarps > warps_needed) g = (warps_needed + kWarps - 1) / kWarps;
+    if (g > kMaxGrid) g = kMaxGrid;
+    if (g < 1) g = 1;
+    bool priv = want_priv;
+    if (hist && priv) {
+        const long long items_per_warp = (p.n_rows + g * kWarps - 1) / (g * kWarps);
+        const long long px_per_lane = items_per_warp * ((tile_w + kRowBlock - 1) / kRowBlock) * kUnroll * 4;
+        if (px_per_lane > 60000) priv = false;  // fall back to shared-memory atomics (no overflow possible)
+    }
+    const int smem = lut_bytes + (hist ? (priv ? BinAcc<true>::smem_bytes(hist_C + 2) : BinAcc<false>::smem_bytes(hist_C + 2)) : 0);
+    if (smem > 48 * 1024) {
+        if (priv) CVCS_CUDA_OK(cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else CVCS_CUDA_OK(cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    const int grid = static_cast<int>(g);
+    if (priv) tile_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+    else tile_kernel<false><<<grid, kThreads, smem, stream>>>(p);
     CVCS_CUDA_OK(cudaGetLastError());
     return CVCS_OK;
 }
