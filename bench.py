@@ -297,7 +297,8 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "tma", "direct", "generic"])
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--no-wait-hint", action="store_true", help="A/B: mbarrier waits without the suspend-time hint")
-    ap.add_argument("--bf16-vecp", type=int, default=0, help="A/B: pixels per thread of the bf16 TMA variant (4 or 8)")
+    ap.add_argument("--ctas", type=int, default=0, help="A/B: CTAs per SM the TMA variant sizes its stages for")
+    ap.add_argument("--vecp", type=int, default=0, help="A/B: pixels per consumer thread of the TMA variant (f32: 2|4, bf16: 4|8)")
     ap.add_argument("--label-dtype", default="u8", choices=["u8", "i64"])
     ap.add_argument("--no-grad", action="store_true", help="forward/eval only (no dlogits)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -336,7 +337,8 @@ def main():
     _lib.set_option(_lib.OPT_CE_PATH, {"auto": 0, "tma": 1, "direct": 2, "generic": 3}[args.path])
     _lib.set_option(_lib.OPT_TMA_STAGES, args.stages)
     _lib.set_option(_lib.OPT_TMA_WAIT_HINT, 1 if args.no_wait_hint else 0)
-    _lib.set_option(_lib.OPT_TMA_BF16_VECP, args.bf16_vecp)
+    _lib.set_option(_lib.OPT_TMA_VECP, args.vecp)
+    _lib.set_option(_lib.OPT_TMA_CTAS, args.ctas)
 
     B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
     esize = 4 if wl["dtype"] == "f32" else 2

@@ -8,7 +8,7 @@ int ce_tma_launch_bf16(const CeParams& p, int layout, cudaStream_t stream, bool*
     *handled = false;
     if (layout == CVCS_NCHW) {
         if (p.C <= 8) {
-            if (get_option(CVCS_OPT_TMA_BF16_VECP) == 4) return tma::dispatch<__nv_bfloat16, 4, false, 2, 8>(p, stream, handled);
+            if (get_option(CVCS_OPT_TMA_VECP) == 4) return tma::dispatch<__nv_bfloat16, 4, false, 2, 8>(p, stream, handled);
             return tma::dispatch<__nv_bfloat16, 8, false, 2, 8>(p, stream, handled);
         }
         if (p.C <= 16) return tma::dispatch<__nv_bfloat16, 4, false, 9, 16>(p, stream, handled);

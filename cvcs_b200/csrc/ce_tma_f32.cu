@@ -7,7 +7,10 @@ namespace cvcs {
 int ce_tma_launch_f32(const CeParams& p, int layout, cudaStream_t stream, bool* handled) {
     *handled = false;
     if (layout == CVCS_NCHW) {
-        if (p.C <= 8) return tma::dispatch<float, 4, false, 2, 8>(p, stream, handled);
+        if (p.C <= 8) {
+            if (get_option(CVCS_OPT_TMA_VECP) == 2) return tma::dispatch<float, 2, false, 2, 8>(p, stream, handled);
+            return tma::dispatch<float, 4, false, 2, 8>(p, stream, handled);
+        }
         if (p.C <= 16) return tma::dispatch<float, 2, false, 9, 16>(p, stream, handled);
         return tma::dispatch<float, 1, false, 17, kMaxRegC>(p, stream, handled);
     }

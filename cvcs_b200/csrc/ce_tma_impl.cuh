@@ -460,9 +460,13 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     g.hist_off = 0;
     const int hist_bytes = p.confmat ? BinAcc<PRIV>::smem_bytes(C * C) : 0;
     g.stage_off = ((hist_bytes + 127) / 128) * 128;
-    // two CTAs per SM: each may use up to ~112 KB of the 227 KB; wide stages (i64 labels, large C)
-    // that would leave fewer than 3 stages get the whole SM instead
-    int stages = (113 * 1024 - g.stage_off) / g.stage_bytes;
+    // CTAs per SM the shared-memory budget is cut for (2 unless overridden): 228 KB per SM, 1 KB
+    // reserved per CTA, ~0.5 KB static.  Wide stages (i64 labels, large C) that would leave fewer
+    // than 3 stages get the whole SM instead.
+    int target_ctas = get_option(CVCS_OPT_TMA_CTAS);
+    if (target_ctas < 1 || target_ctas > 4) target_ctas = 2;
+    const int per_cta = 233472 / target_ctas - 1024 - 512;
+    int stages = (per_cta - g.stage_off) / g.stage_bytes;
     if (stages < 3) stages = (226 * 1024 - g.stage_off) / g.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     const int want_stages = get_option(CVCS_OPT_TMA_STAGES);

@@ -90,8 +90,9 @@ enum cvcs_option {
     CVCS_OPT_CE_PATH = 0,    /* cvcs_ce_fused variant: 0 auto, 1 TMA-staged, 2 direct-load, 3 generic */
     CVCS_OPT_TMA_STAGES = 1, /* TMA-staged variant: pipeline depth (0 = as many as fit, max 8)        */
     CVCS_OPT_TMA_WAIT_HINT = 2, /* 0: mbarrier waits pass a long suspend-time hint (default), 1: no hint */
-    CVCS_OPT_TMA_BF16_VECP = 3, /* bf16 NCHW, C <= 8: pixels per thread, 0 = default, 4 or 8            */
-    CVCS_OPT_COUNT = 4
+    CVCS_OPT_TMA_VECP = 3,   /* NCHW, C <= 8: pixels per consumer thread (0 = default; f32: 2|4, bf16: 4|8) */
+    CVCS_OPT_TMA_CTAS = 4,   /* CTAs per SM the TMA variant sizes its stages for (0 = default 2; 1..4)      */
+    CVCS_OPT_COUNT = 5
 };
 int cvcs_set_option(int option, int value);
 

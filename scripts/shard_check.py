@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""N-rank NCCL check of cvcs_b200.shard.ShardedScenePass (cfg4-style): tile-sharded scenes, global
+loss and confusion matrix must equal the single-rank result on all tiles.  Run under torchrun."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cvcs_b200 import shard  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    C, p, n_scenes, HW = 7, 256, 3, 1100                     # 4 x 4 = 16 whole tiles per scene
+    g = torch.Generator().manual_seed(0)
+    scenes = []
+    for s in range(n_scenes):
+        img = torch.randint(0, 256, (3, HW, HW), generator=g, dtype=torch.uint8)
+        lab = torch.randint(0, C, (HW // 20, HW // 20), generator=g, dtype=torch.uint8).repeat_interleave(20, 0).repeat_interleave(20, 1)
+        lab[torch.rand(HW, HW, generator=g) < 0.1] = 255
+        scenes.append((img, lab.contiguous()))
+    proj = (torch.randn(C, 3, generator=g) * 0.02).to(dev)
+
+    def logits_fn(x, y):                                      # a stub "segmenter": per-pixel linear map of the bands
+        return torch.einsum("kc,bchw->bkhw", proj, x).contiguous()
+
+    weight = (torch.arange(C, dtype=torch.float32) + 1).to(dev) / C
+    results = {}
+    for policy in ("round_robin", "scene"):
+        sp = shard.ShardedScenePass(scenes, p, C, logits_fn, weight=weight, ignore_index=255, batch_size=8, device=dev,
+                                    policy=policy, want_grad=True).run()
+        loss, cm = sp.finish()
+        results[policy] = (float(loss), cm)
+    # single-rank reference on rank 0 only (a sub-group of one rank -> no collectives)
+    if rank == 0:
+        solo = dist.new_group([0]) if world > 1 else None
+    else:
+        solo = None
+    if world > 1:
+        dist.barrier()
+    ok = True
+    if rank == 0:
+        class One:
+            pass
+        sp1 = shard.ShardedScenePass(scenes, p, C, logits_fn, weight=weight, ignore_index=255, batch_size=8, device=dev,
+                                     want_grad=True)
+        sp1.rank, sp1.world = 0, 1
+        sp1.tiles = shard.local_tiles(n_scenes, sp1.image_shape, p, 0, 1)
+        sp1.group = solo
+        # run without collectives: world_info(group) of a 1-rank group is (0, 1)
+        sp1.run()
+        l1 = float((sp1.sums[0] / sp1.sums[1]).item())
+        cm1 = sp1.confmat.cpu()
+        for policy, (l, cm) in results.items():
+            same_cm = bool(torch.equal(cm, cm1))
+            rel = abs(l - l1) / abs(l1)
+            print(f"{policy}: loss {l:.7f} vs single-rank {l1:.7f} (rel {rel:.2e}); confusion equal: {same_cm}; tiles {int(cm.sum())}")
+            ok &= same_cm and rel < 1e-6
+        print("SHARD CHECK", "OK" if ok else "FAILED", f"world={world}")
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
