@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcvcs_b200.so")
+# CVCS_B200_LIB selects an experiment build (python -m cvcs_b200.build --tag X -D...) for A/B timing runs
+LIB_PATH = os.environ.get("CVCS_B200_LIB") or os.path.join(_PKG, "libcvcs_b200.so")
 
 # dtype / layout tags (enum cvcs_dtype / cvcs_layout)
 F32, BF16, U8, I64, I32 = 0, 1, 2, 3, 4

@@ -67,10 +67,16 @@ def _headers() -> list[str]:
     return hs
 
 
-def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, defines=(), tag: str = "") -> str:
+    """defines / tag: experiment builds (`-DNAME` flags) go to libcvcs_b200_<tag>.so with their own
+    object directory; the default build takes neither."""
+    global OBJ_DIR, LIB_PATH
+    if tag:
+        OBJ_DIR = os.path.join(PKG_DIR, "build_" + tag)
+        LIB_PATH = os.path.join(PKG_DIR, f"libcvcs_b200_{tag}.so")
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
-    flags = NVCC_FLAGS + ARCH_FLAGS + (["-Xptxas", "-v"] if ptxas_info else [])
+    flags = NVCC_FLAGS + ARCH_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + [f"-D{d}" for d in defines]
     headers = _headers()
     jobs = []
     objs = []
@@ -116,8 +122,10 @@ def main() -> None:
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--ptxas-info", action="store_true", help="pass -Xptxas -v (registers, spills, smem)")
+    ap.add_argument("-D", dest="defines", action="append", default=[], help="experiment build: extra -D define")
+    ap.add_argument("--tag", default="", help="experiment build: library suffix")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose, ptxas_info=a.ptxas_info))
+    print(build(force=a.force, verbose=a.verbose, ptxas_info=a.ptxas_info, defines=a.defines, tag=a.tag))
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@
 namespace cvcs {
 namespace tma {
 
-constexpr int kProducerWarps = 1;
+constexpr int kProducerWarps = 2;  // warp 8: bulk loads, warp 9: bulk stores
 constexpr int kBlock = kThreads + 32 * kProducerWarps;
 constexpr int kMaxStages = 8;
 constexpr int kConsumerBar = 1;  // named barrier of the 256 consumer threads
@@ -43,6 +43,19 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
     constexpr int ES = sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ float wsm[C];
-    __shared__ __align__(8) unsigned long long bars[2 * kMaxStages];  // full[S], done[S]
+    __shared__ __align__(8) unsigned long long bars[3 * kMaxStages];  // full[S], done[S], free[S]
 
     const int tid = threadIdx.x;
     constexpr bool do_grad = GRAD;
@@ -189,8 +202,13 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(bar0 + 8 * s, 1);                       // full: producer's expect_tx arrive
+            mbar_init(bar0 + 8 * s, 1);                       // full: loader's expect_tx arrive
+            mbar_init(bar0 + 8 * (2 * kMaxStages + s), 1);    // free: the store warp, once the stage has left smem
+#ifdef CVCS_X_WARPARRIVE
+            mbar_init(bar0 + 8 * (kMaxStages + s), kThreads / 32);
+#else
             mbar_init(bar0 + 8 * (kMaxStages + s), kThreads);  // done: every consumer thread
+#endif
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
@@ -205,14 +223,32 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
     unsigned int bad = 0;
 
     if (tid >= kThreads) {
-        // ================= producer =================
+        // ================= producers: one lane of warp 8 loads, one lane of warp 9 stores =================
+        // A stage cycles  load -> full -> (consumers) -> done -> store -> free -> load ...  The two
+        // roles never wait on each other's work except through the barriers, so a stage is refilled
+        // as soon as its gradients have left shared memory, however long the consumers take.
+        const T* __restrict__ logits = reinterpret_cast<const T*>(p.logits);
+        T* __restrict__ dlogits = reinterpret_cast<T*>(p.dlogits);
+        const unsigned char* __restrict__ target = reinterpret_cast<const unsigned char*>(p.target);
+        auto wait = [&](uint32_t bar, uint32_t phase) {
+            if (g.wait_hint) mbar_wait<true>(bar, phase);
+            else mbar_wait<false>(bar, phase);
+        };
         if (tid == kThreads) {
-            const T* __restrict__ logits = reinterpret_cast<const T*>(p.logits);
-            T* __restrict__ dlogits = reinterpret_cast<T*>(p.dlogits);
-            const unsigned char* __restrict__ target = reinterpret_cast<const unsigned char*>(p.target);
-            auto issue_load = [&](const Chunk& ck, int s) {
-                const uint32_t dst = stage0 + s * g.stage_bytes;
-                const uint32_t bar = bar0 + 8 * s;
+            // ---- loader
+            ChunkWalker<C, P, NHWC> ld;
+            ld.init(p);
+            Ring ring{0, 0u};
+            for (long long i = 0; i < mine; ++i) {
+                if (i >= S) {
+                    // the stage's previous occupant: stored away (grad) / consumed (forward only)
+                    const uint32_t prev = ring.phase ^ 1u;
+                    if constexpr (do_grad) wait(bar0 + 8 * (2 * kMaxStages + ring.s), prev);
+                    else wait(bar0 + 8 * (kMaxStages + ring.s), prev);
+                }
+                const Chunk ck = ld.get(p);
+                const uint32_t dst = stage0 + ring.s * g.stage_bytes;
+                const uint32_t bar = bar0 + 8 * ring.s;
                 const uint32_t lbytes = static_cast<uint32_t>(ck.n) * tsize;
                 mbar_expect_tx(bar, static_cast<uint32_t>(ck.n) * C * ES + lbytes);
                 if constexpr (NHWC) {
@@ -223,9 +259,26 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                         bulk_g2s(dst + c * P * ES, logits + ck.elem0 + c * p.hw, static_cast<uint32_t>(ck.n) * ES, bar);
                 }
                 bulk_g2s(dst + g.label_off, target + ck.pix0 * tsize, lbytes, bar);
-            };
-            auto issue_store = [&](const Chunk& ck, int s) {
-                const uint32_t src = stage0 + s * g.stage_bytes;
+                ld.next();
+                ring.next(S);
+            }
+        } else if (do_grad && tid == kThreads + 32) {
+            // ---- storer: up to two bulk stores in flight; a stage is handed back to the loader as soon
+            // as its store has finished reading shared memory — before blocking on the next `done`
+            ChunkWalker<C, P, NHWC> st;
+            st.init(p);
+            Ring ring{0, 0u};
+            int pending = -1;  // stage whose store has been issued but not yet waited for
+            for (long long i = 0; i < mine; ++i) {
+                const uint32_t done = bar0 + 8 * (kMaxStages + ring.s);
+                if (pending >= 0 && !mbar_test(done, ring.phase)) {
+                    bulk_wait_read<0>();
+                    mbar_arrive(bar0 + 8 * (2 * kMaxStages + pending));
+                    pending = -1;
+                }
+                wait(done, ring.phase);
+                const Chunk ck = st.get(p);
+                const uint32_t src = stage0 + ring.s * g.stage_bytes;
                 if constexpr (NHWC) {
                     bulk_s2g(dlogits + ck.elem0, src, static_cast<uint32_t>(ck.n) * C * ES);
                 } else {
@@ -234,42 +287,15 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                         bulk_s2g(dlogits + ck.elem0 + c * p.hw, src + c * P * ES, static_cast<uint32_t>(ck.n) * ES);
                 }
                 bulk_commit();
-            };
-            // `ld` runs ahead of `st` by up to S chunks
-            ChunkWalker<C, P, NHWC> ld, st;
-            ld.init(p);
-            st.init(p);
-            Ring ld_ring{0, 0u}, st_ring{0, 0u};
-            long long loaded = 0;
-            const long long pre = mine < S ? mine : S;
-            for (; loaded < pre; ++loaded) {
-                issue_load(ld.get(p), ld_ring.s);
-                ld.next();
-                ld_ring.next(S);
-            }
-            for (long long i = 0; i < mine; ++i) {
-                if (g.wait_hint) mbar_wait<true>(bar0 + 8 * (kMaxStages + st_ring.s), st_ring.phase);
-                else mbar_wait<false>(bar0 + 8 * (kMaxStages + st_ring.s), st_ring.phase);
-                if (do_grad) {
-                    issue_store(st.get(p), st_ring.s);
-                    // the stage consumed one step earlier is free once its store has left smem
-                    if (i >= 1 && loaded < mine) {
-                        bulk_wait_read<1>();
-                        issue_load(ld.get(p), ld_ring.s);
-                        ld.next();
-                        ld_ring.next(S);
-                        ++loaded;
-                    }
-                } else if (loaded < mine) {
-                    issue_load(ld.get(p), ld_ring.s);
-                    ld.next();
-                    ld_ring.next(S);
-                    ++loaded;
+                if (pending >= 0) {
+                    bulk_wait_read<1>();                                  // the older store has left shared memory
+                    mbar_arrive(bar0 + 8 * (2 * kMaxStages + pending));    // -> the loader may refill that stage
                 }
+                pending = ring.s;
                 st.next();
-                st_ring.next(S);
+                ring.next(S);
             }
-            if (do_grad) bulk_wait_all();
+            bulk_wait_all();
         }
     } else {
         // ================= consumers =================
@@ -364,14 +390,22 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                     bad += (!valid && tv != -1) ? 1u : 0u;
                     const int tc = valid ? tv : 0;
                     // the target logit and its class weight by dynamic index from shared memory
+#ifndef CVCS_X_NOFIX
                     const float xt = lds_elem<T>(stage, eidx(tc, pix_t0 + k));
+#else
+                    const float xt = raw_get(ridx(0, k));
+#endif
                     const float w = valid ? wsm[tc] : 0.f;
                     float x[C];
 #pragma unroll
                     for (int c = 0; c < C; ++c) x[c] = raw_get(ridx(c, k));
                     float m, s;
                     int arg;
+#ifndef CVCS_X_NOMATH
                     softmax_core<C>(x, m, s, arg);
+#else
+                    m = x[0]; s = 1.f + x[1]; arg = 0;
+#endif
                     anomalous |= (s != s);
                     amax[k] = arg;
                     const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
@@ -394,8 +428,12 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                         }
                     }
                 }
+#ifndef CVCS_X_NOLOSS
                 lsum += static_cast<double>(step_l);
                 wsum += static_cast<double>(step_w);
+#else
+                if (step_l == 123.456f) lsum += step_w;
+#endif
                 // rows with NaN / inf (rare): redo the argmax with torch's NaN rule from the original
                 // logits, which are still in the stage
                 if (anomalous) {
@@ -403,11 +441,13 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                     for (int k = 0; k < VECP; ++k)
                         amax[k] = argmax_nan_aware<C>([&](int c) { return lds_elem<T>(stage, eidx(c, pix_t0 + k)); });
                 }
+#ifndef CVCS_X_NOCONF
                 if (do_conf) {
 #pragma unroll
                     for (int k = 0; k < VECP; ++k)
                         if (static_cast<unsigned int>(t[k]) < static_cast<unsigned int>(C)) conf.add(t[k] * C + amax[k]);
                 }
+#endif
                 // ---- registers -> shared (in place), then the target-class entries
                 if constexpr (do_grad) {
                     if constexpr (NHWC) {
@@ -423,14 +463,23 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                             else *reinterpret_cast<uint32_t*>(dst) = raw[c];
                         }
                     }
+#ifndef CVCS_X_NOFIX
 #pragma unroll
                     for (int k = 0; k < VECP; ++k)
                         if (static_cast<unsigned int>(t[k]) < static_cast<unsigned int>(C)) sts_elem<T>(stage, eidx(t[k], pix_t0 + k), gfix[k]);
+#endif
                 }
+#ifndef CVCS_X_NOARG
                 if (do_arg) store_argmax<VECP>(p, ck.pix0 + pix_t0, amax);
+#endif
             }
             if constexpr (do_grad) fence_async_smem();  // make the in-place gradients visible to the bulk store
+#ifdef CVCS_X_WARPARRIVE
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar0 + 8 * (kMaxStages + ring.s));
+#else
             mbar_arrive(bar0 + 8 * (kMaxStages + ring.s));
+#endif
             if (PRIV && do_conf) {
                 since_flush += VECP;
                 if (since_flush > 65535u - VECP) {

@@ -123,7 +123,7 @@ class ShardedScenePass:
     def __init__(self, scenes, p: int, num_classes: int, logits_fn, *, weight: Optional[torch.Tensor] = None,
                  ignore_index: int = -100, batch_size: int = 16, device=None, group=None, policy: str = "round_robin",
                  mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None,
-                 tile_dtype: torch.dtype = torch.float32, want_grad: bool = False):
+                 tile_dtype: torch.dtype = torch.float32, want_grad: bool = False, single_process: bool = False):
         from . import ops
         self.ops = ops
         self.scenes, self.p, self.C, self.logits_fn = scenes, p, num_classes, logits_fn
@@ -131,7 +131,9 @@ class ShardedScenePass:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.group, self.policy = group, policy
         self.mean, self.std, self.tile_dtype, self.want_grad = mean, std, tile_dtype, want_grad
-        self.rank, self.world = world_info(group)
+        # single_process: ignore torch.distributed (this process takes every tile, no collectives)
+        self.single = single_process
+        self.rank, self.world = (0, 1) if single_process else world_info(group)
         self.image_shape = list(scenes[0][0].shape[1:])
         self.tiles = local_tiles(len(scenes), self.image_shape, p, self.rank, self.world, policy)
         dev = self.device
@@ -158,7 +160,10 @@ class ShardedScenePass:
         inv_tw_dev = None
         if self.want_grad:
             self._label_hist_pass()
-            tw = global_total_weight(self.hist, self.weight, self.C, self.ignore_index, self.group)   # collective (1)
+            if self.single:
+                tw = ops.total_weight(self.hist, self.weight, self.C, self.ignore_index)
+            else:
+                tw = global_total_weight(self.hist, self.weight, self.C, self.ignore_index, self.group)   # collective (1)
             inv_tw_dev = tw[1:]
         step_sums = torch.empty(3, dtype=torch.float64, device=dev)
         cache = {}
@@ -186,6 +191,10 @@ class ShardedScenePass:
 
     def finish(self):
         """Collectives (2) and (3).  Returns (global loss f32 0-dim, global confusion int64[C,C] on the host)."""
+        if self.single:
+            loss = (self.sums[0] / self.sums[1]).to(torch.float32)
+            loss = torch.where(self.sums[2] > 0, torch.full_like(loss, float("nan")), loss)
+            return loss, self.confmat.cpu()
         loss = global_loss(self.sums, self.group)
         cm = global_confmat(self.confmat, self.group)
         return loss, cm.cpu()

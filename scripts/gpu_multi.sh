@@ -9,5 +9,5 @@ tail -1 gpurun_out/bench_${wl}_n$N.log | cut -c1-600
 done
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > gpurun_out/bench_ref_n$N.log 2>&1; echo "ref n$N rc=$?" | tee -a gpurun_out/summary_multi.txt
 tail -1 gpurun_out/bench_ref_n$N.log | cut -c1-300
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 scripts/shard_check.py > gpurun_out/shard_check_n$N.log 2>&1; echo "shard_check n$N rc=$?" | tee -a gpurun_out/summary_multi.txt
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 scripts/shard_check.py > gpurun_out/shard_check_n$N.log 2>&1; echo "shard_check n$N rc=$?" | tee -a gpurun_out/summary_multi.txt
 tail -3 gpurun_out/shard_check_n$N.log

@@ -36,31 +36,19 @@ def main():
                                     policy=policy, want_grad=True).run()
         loss, cm = sp.finish()
         results[policy] = (float(loss), cm)
-    # single-rank reference on rank 0 only (a sub-group of one rank -> no collectives)
-    if rank == 0:
-        solo = dist.new_group([0]) if world > 1 else None
-    else:
-        solo = None
-    if world > 1:
-        dist.barrier()
+    # single-process reference: every rank redoes ALL tiles with collectives switched off
+    sp1 = shard.ShardedScenePass(scenes, p, C, logits_fn, weight=weight, ignore_index=255, batch_size=8, device=dev,
+                                 want_grad=True, single_process=True).run()
+    l1_t, cm1 = sp1.finish()
+    l1 = float(l1_t)
     ok = True
+    for policy, (l, cm) in results.items():
+        same_cm = bool(torch.equal(cm, cm1))
+        rel = abs(l - l1) / abs(l1)
+        if rank == 0:
+            print(f"{policy}: loss {l:.7f} vs single-process {l1:.7f} (rel {rel:.2e}); confusion equal: {same_cm}; pixels {int(cm.sum())}")
+        ok &= same_cm and rel < 1e-6
     if rank == 0:
-        class One:
-            pass
-        sp1 = shard.ShardedScenePass(scenes, p, C, logits_fn, weight=weight, ignore_index=255, batch_size=8, device=dev,
-                                     want_grad=True)
-        sp1.rank, sp1.world = 0, 1
-        sp1.tiles = shard.local_tiles(n_scenes, sp1.image_shape, p, 0, 1)
-        sp1.group = solo
-        # run without collectives: world_info(group) of a 1-rank group is (0, 1)
-        sp1.run()
-        l1 = float((sp1.sums[0] / sp1.sums[1]).item())
-        cm1 = sp1.confmat.cpu()
-        for policy, (l, cm) in results.items():
-            same_cm = bool(torch.equal(cm, cm1))
-            rel = abs(l - l1) / abs(l1)
-            print(f"{policy}: loss {l:.7f} vs single-rank {l1:.7f} (rel {rel:.2e}); confusion equal: {same_cm}; tiles {int(cm.sum())}")
-            ok &= same_cm and rel < 1e-6
         print("SHARD CHECK", "OK" if ok else "FAILED", f"world={world}")
     dist.barrier()
     dist.destroy_process_group()
