@@ -210,6 +210,8 @@ def run_tile_bench(args, wl):
     import torch
     from cvcs_b200 import ops
     from oracle import torch_path
+    from cvcs_b200 import _lib
+    _lib.set_option(_lib.OPT_TILE_CTAS, args.ctas)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     B, Cb, p, S = wl["B"], wl["Cb"], wl["H"], wl["scene"]

@@ -147,11 +147,20 @@ __device__ __forceinline__ int argmax_nan_aware(F&& fetch) {
     return arg;
 }
 
+// exp(x - m) for x <= m.  FUSED (bf16 logits, 1e-2 tolerance): one FFMA + MUFU, x*log2e - m*log2e,
+// whose rounding error in the exponent is <= ulp(m*log2e)/2 (about 1e-6 relative for |m| ~ 20);
+// otherwise the subtraction is done first and is exact for nearby values: FADD + FMUL + MUFU.
+template <bool FUSED>
+__device__ __forceinline__ float exp_shifted(float x, float m) {
+    if constexpr (FUSED) return ex2_ftz(fmaf(x, kLog2e, -m * kLog2e));
+    else return ex2_ftz((x - m) * kLog2e);
+}
+
 // Softmax statistics of one pixel.  On exit x[c] = exp(x[c] - max), m = max (NaNs skipped),
 // s = Σ x[c], and arg = first index with x[c] == max, which is torch's argmax whenever the row
 // holds no NaN / +inf / all -inf; those rows give s = NaN and the caller redoes the argmax with
 // argmax_nan_aware on the original values.
-template <int C>
+template <int C, bool FUSED = false>
 __device__ __forceinline__ void softmax_core(float (&x)[C], float& m, float& s, int& arg) {
     m = x[0];
 #pragma unroll
@@ -162,7 +171,7 @@ __device__ __forceinline__ void softmax_core(float (&x)[C], float& m, float& s, 
     s = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        x[c] = ex2_ftz((x[c] - m) * kLog2e);
+        x[c] = exp_shifted<FUSED>(x[c], m);
         s += x[c];
     }
 }

@@ -184,7 +184,7 @@ __device__ __forceinline__ void sts_elem(unsigned char* base, int idx, float v) 
 }
 
 template <typename T, int C, int VECP, bool NHWC, bool PRIV, bool GRAD>
-__global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const Geom g) {
+__global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, const Geom g) {
     constexpr int P = kThreads * VECP;
     constexpr int ES = sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
@@ -204,11 +204,7 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
         for (int s = 0; s < S; ++s) {
             mbar_init(bar0 + 8 * s, 1);                       // full: loader's expect_tx arrive
             mbar_init(bar0 + 8 * (2 * kMaxStages + s), 1);    // free: the store warp, once the stage has left smem
-#ifdef CVCS_X_WARPARRIVE
-            mbar_init(bar0 + 8 * (kMaxStages + s), kThreads / 32);
-#else
             mbar_init(bar0 + 8 * (kMaxStages + s), kThreads);  // done: every consumer thread
-#endif
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
@@ -378,62 +374,62 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                         t[k] = (v == ign8) ? -1 : v;
                     }
                 }
-                // ---- math, one pixel at a time (the compiler interleaves the unrolled pixels)
+                // ---- math.  fp32: one pixel at a time; bf16 NCHW: two pixels at a time, because a 32-bit
+                // word of a class plane holds the pixel pair (2j, 2j+1) and both gradients are packed with one
+                // cvt.rn.bf16x2 (the compiler interleaves the unrolled groups either way)
+                constexpr int PP = (ES == 2 && !NHWC && VECP % 2 == 0) ? 2 : 1;
                 int amax[VECP];
                 float gfix[VECP];     // gradient of the target class, patched into the stage afterwards
                 float step_l = 0.f, step_w = 0.f;
                 bool anomalous = false;  // some pixel's Σexp is NaN (NaN / +inf / all -inf logits)
 #pragma unroll
-                for (int k = 0; k < VECP; ++k) {
-                    const int tv = t[k];
-                    const bool valid = static_cast<unsigned int>(tv) < static_cast<unsigned int>(C);
-                    bad += (!valid && tv != -1) ? 1u : 0u;
-                    const int tc = valid ? tv : 0;
-                    // the target logit and its class weight by dynamic index from shared memory
-#ifndef CVCS_X_NOFIX
-                    const float xt = lds_elem<T>(stage, eidx(tc, pix_t0 + k));
-#else
-                    const float xt = raw_get(ridx(0, k));
-#endif
-                    const float w = valid ? wsm[tc] : 0.f;
-                    float x[C];
+                for (int k0 = 0; k0 < VECP; k0 += PP) {
+                    float x[PP][C];
+                    float r[PP];
 #pragma unroll
-                    for (int c = 0; c < C; ++c) x[c] = raw_get(ridx(c, k));
-                    float m, s;
-                    int arg;
-#ifndef CVCS_X_NOMATH
-                    softmax_core<C>(x, m, s, arg);
-#else
-                    m = x[0]; s = 1.f + x[1]; arg = 0;
-#endif
-                    anomalous |= (s != s);
-                    amax[k] = arg;
-                    const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
-                    step_l += valid ? w * nll : 0.f;
-                    step_w += w;
+                    for (int q = 0; q < PP; ++q) {
+                        const int k = k0 + q;
+                        const int tv = t[k];
+                        const bool valid = static_cast<unsigned int>(tv) < static_cast<unsigned int>(C);
+                        bad += (!valid && tv != -1) ? 1u : 0u;
+                        const int tc = valid ? tv : 0;
+                        // the target logit and its class weight by dynamic index from shared memory
+                        const float xt = lds_elem<T>(stage, eidx(tc, pix_t0 + k));
+                        const float w = valid ? wsm[tc] : 0.f;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) x[q][c] = raw_get(ridx(c, k));
+                        float m, s;
+                        int arg;
+                        softmax_core<C, ES == 2>(x[q], m, s, arg);
+                        anomalous |= (s != s);
+                        amax[k] = arg;
+                        const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
+                        step_l += valid ? w * nll : 0.f;
+                        step_w += w;
+                        r[q] = 0.f;
+                        if constexpr (do_grad) {
+                            const float gsc = valid ? w * inv_tw : 0.f;  // exact zeros at ignored pixels
+                            r[q] = gsc * rcp_ftz(s);
+                            gfix[k] = fmaf(exp_shifted<ES == 2>(xt, m), r[q], -gsc);
+                        }
+                    }
                     if constexpr (do_grad) {
-                        const float gsc = valid ? w * inv_tw : 0.f;  // exact zeros at ignored pixels
-                        const float r = gsc * rcp_ftz(s);
-                        gfix[k] = fmaf(ex2_ftz((xt - m) * kLog2e), r, -gsc);
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
-                            const float gv = x[c] * r;
-                            const int e = ridx(c, k);
                             if constexpr (ES == 4) {
-                                raw[e] = __float_as_uint(gv);
-                            } else {  // bf16: RNE, merged into the half of the word this pixel owns
-                                const uint32_t h = pack_bf16(gv, 0.f) & 0xffffu;
+                                raw[ridx(c, k0)] = __float_as_uint(x[0][c] * r[0]);
+                            } else if constexpr (PP == 2) {
+                                raw[ridx(c, k0) >> 1] = pack_bf16(x[0][c] * r[0], x[PP - 1][c] * r[PP - 1]);
+                            } else {  // bf16 NHWC: RNE, merged into the half of the word this element owns
+                                const int e = ridx(c, k0);
+                                const uint32_t h = pack_bf16(x[0][c] * r[0], 0.f) & 0xffffu;
                                 raw[e >> 1] = (e & 1) ? ((raw[e >> 1] & 0x0000ffffu) | (h << 16)) : ((raw[e >> 1] & 0xffff0000u) | h);
                             }
                         }
                     }
                 }
-#ifndef CVCS_X_NOLOSS
                 lsum += static_cast<double>(step_l);
                 wsum += static_cast<double>(step_w);
-#else
-                if (step_l == 123.456f) lsum += step_w;
-#endif
                 // rows with NaN / inf (rare): redo the argmax with torch's NaN rule from the original
                 // logits, which are still in the stage
                 if (anomalous) {
@@ -441,13 +437,11 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                     for (int k = 0; k < VECP; ++k)
                         amax[k] = argmax_nan_aware<C>([&](int c) { return lds_elem<T>(stage, eidx(c, pix_t0 + k)); });
                 }
-#ifndef CVCS_X_NOCONF
                 if (do_conf) {
 #pragma unroll
                     for (int k = 0; k < VECP; ++k)
                         if (static_cast<unsigned int>(t[k]) < static_cast<unsigned int>(C)) conf.add(t[k] * C + amax[k]);
                 }
-#endif
                 // ---- registers -> shared (in place), then the target-class entries
                 if constexpr (do_grad) {
                     if constexpr (NHWC) {
@@ -463,23 +457,14 @@ __global__ void __launch_bounds__(kBlock) ce_tma_kernel(const CeParams p, const 
                             else *reinterpret_cast<uint32_t*>(dst) = raw[c];
                         }
                     }
-#ifndef CVCS_X_NOFIX
 #pragma unroll
                     for (int k = 0; k < VECP; ++k)
                         if (static_cast<unsigned int>(t[k]) < static_cast<unsigned int>(C)) sts_elem<T>(stage, eidx(t[k], pix_t0 + k), gfix[k]);
-#endif
                 }
-#ifndef CVCS_X_NOARG
                 if (do_arg) store_argmax<VECP>(p, ck.pix0 + pix_t0, amax);
-#endif
             }
             if constexpr (do_grad) fence_async_smem();  // make the in-place gradients visible to the bulk store
-#ifdef CVCS_X_WARPARRIVE
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(bar0 + 8 * (kMaxStages + ring.s));
-#else
             mbar_arrive(bar0 + 8 * (kMaxStages + ring.s));
-#endif
             if (PRIV && do_conf) {
                 since_flush += VECP;
                 if (since_flush > 65535u - VECP) {
@@ -509,24 +494,35 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     g.hist_off = 0;
     const int hist_bytes = p.confmat ? BinAcc<PRIV>::smem_bytes(C * C) : 0;
     g.stage_off = ((hist_bytes + 127) / 128) * 128;
-    // CTAs per SM the shared-memory budget is cut for (2 unless overridden): 228 KB per SM, 1 KB
-    // reserved per CTA, ~0.5 KB static.  Wide stages (i64 labels, large C) that would leave fewer
-    // than 3 stages get the whole SM instead.
+    // Pipeline geometry (measured on B200).  With gradients (read + write streams) the
+    // sustained HBM rate peaks when the stages resident on an SM total ~90-125 KB and falls off on either
+    // side (59 KB: 0.74, 89 KB: 0.90, 119 KB: 0.84, 178 KB: 0.83 of the measured copy peak for fp32 C=7):
+    // 3 stages per CTA, and 2 CTAs per SM only while 2 x 3 stages stay within 128 KB.  Forward-only
+    // (read stream only) wants as much in flight as fits: 2 CTAs, as many stages as the budget allows.
+    const bool grad = p.dlogits != nullptr;
     int target_ctas = get_option(CVCS_OPT_TMA_CTAS);
-    if (target_ctas < 1 || target_ctas > 4) target_ctas = 2;
-    const int per_cta = 233472 / target_ctas - 1024 - 512;
+    if (target_ctas < 1 || target_ctas > 4) target_ctas = (grad && 2 * 3 * g.stage_bytes > 128 * 1024) ? 1 : 2;
+    const int per_cta = 233472 / target_ctas - 1024 - 1024;  // 228 KB per SM, 1 KB reserved per CTA, static smem
     int stages = (per_cta - g.stage_off) / g.stage_bytes;
-    if (stages < 3) stages = (226 * 1024 - g.stage_off) / g.stage_bytes;
+    if (stages < 3 && target_ctas > 1) {  // wide stages (i64 labels, large C): the whole SM
+        target_ctas = 1;
+        stages = (226 * 1024 - g.stage_off) / g.stage_bytes;
+    }
+    if (grad && stages > 3) stages = 3;
     if (stages > kMaxStages) stages = kMaxStages;
     const int want_stages = get_option(CVCS_OPT_TMA_STAGES);
-    if (want_stages >= 2 && want_stages <= kMaxStages && want_stages <= stages) stages = want_stages;
+    if (want_stages >= 2 && want_stages <= kMaxStages && want_stages <= (per_cta - g.stage_off) / g.stage_bytes) stages = want_stages;
     if (stages < 2) {  // not even double-buffered: leave the shape to the direct / generic variants
         *handled = false;
         return CVCS_OK;
     }
     g.stages = stages;
     g.wait_hint = get_option(CVCS_OPT_TMA_WAIT_HINT) == 1 ? 0 : 1;
-    const int smem = g.stage_off + stages * g.stage_bytes;
+    int smem = g.stage_off + stages * g.stage_bytes;
+    // keep exactly `target_ctas` CTAs resident: the dynamic request is padded past what target + 1 could share
+    // (more bytes in flight per SM than ~120 KB measurably lowers the sustained HBM rate)
+    const int min_smem = 233472 / (target_ctas + 1) - 1024 + 16;
+    if (smem < min_smem) smem = min_smem;
     auto kernel = p.dlogits ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, true> : ce_tma_kernel<T, C, VECP, NHWC, PRIV, false>;
     int grid = 0;
     int rc = persistent_grid(kernel, kBlock, smem, &grid);

@@ -255,13 +255,13 @@ struct BinAcc {
         }
         sync();
     }
-    __device__ __forceinline__ void add(int key) {
+    __device__ __forceinline__ void add(int key, unsigned int n = 1u) {
         if constexpr (PRIV) {
             unsigned short* c = cnt16 + key * kThreads + threadIdx.x;
-            *c = static_cast<unsigned short>(*c + 1);
+            *c = static_cast<unsigned short>(*c + n);
         } else {
-            if (reps) atomicAdd(bins32 + ((threadIdx.x >> 5) & (reps - 1)) * nb + key, 1u);
-            else atomicAdd(direct + key, 1ull);
+            if (reps) atomicAdd(bins32 + ((threadIdx.x >> 5) & (reps - 1)) * nb + key, n);
+            else atomicAdd(direct + key, static_cast<unsigned long long>(n));
         }
     }
     static __host__ __device__ int smem_bytes(int nbins, int replicas = kWarps) {

@@ -61,21 +61,36 @@ __global__ void __launch_bounds__(kThreads) label_hist_kernel(const HistParams p
         const uint8_t* __restrict__ tgt = reinterpret_cast<const uint8_t*>(p.target);
         const int ign_outside = (p.ignore_index >= C && p.ignore_index <= 255) ? static_cast<int>(p.ignore_index) : -1;
         const long long n16 = p.n / 16;  // pointer is 16-byte aligned (checked on the host)
-        for (long long base = static_cast<long long>(blockIdx.x) * kThreads; base < n16;
-             base += static_cast<long long>(gridDim.x) * kThreads) {
-            const long long i = base + threadIdx.x;
-            if (i < n16) {
-                Raw<16> r;
-                r.load(tgt + 16 * i);
+        // label maps have long runs: a 32-bit word whose four bytes agree is one +4 update
+        auto add_word = [&](uint32_t w) {
+            const int t0 = static_cast<int>(w & 0xff);
+            if (w == static_cast<uint32_t>(t0) * 0x01010101u) {
+                acc.add(hist_bin_u8(t0, C, ign_outside), 4);
+            } else {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int t = (r.word(k / 4) >> (8 * (k % 4))) & 0xff;
-                    acc.add(hist_bin_u8(t, C, ign_outside));
-                }
+                for (int k = 0; k < 4; ++k) acc.add(hist_bin_u8(static_cast<int>((w >> (8 * k)) & 0xff), C, ign_outside), 1);
+            }
+        };
+        constexpr int U = 2;  // independent 128-bit loads in flight per thread
+        const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+        for (long long base = static_cast<long long>(blockIdx.x) * kThreads; base < n16; base += U * stride) {
+            Raw<16> r[U];
+            bool have[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long i = base + u * stride + threadIdx.x;
+                have[u] = i < n16;
+                if (have[u]) r[u].load(tgt + 16 * i);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!have[u]) continue;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) add_word(r[u].word(k));
             }
             if (PRIV) {
-                since_flush += 16;
-                if (since_flush > 65535u - 16u) {
+                since_flush += 16 * U;
+                if (since_flush > 65535u - 16u * U) {
                     acc.flush(p.ws->hist);
                     since_flush = 0;
                 }
@@ -413,8 +428,12 @@ int label_hist_launch(const void* target, int target_dtype, long long n, int C, 
     p.ignore_index = ignore_index;
     p.C = C;
     p.target_i64 = target_dtype == CVCS_I64;
-    const int per = p.target_i64 ? 2 : 16;
-    const long long blocks = (n / per + kThreads - 1) / kThreads;
+    const int per = p.target_i64 ? 2 : 32;  // pixels per thread per step (u8: two 128-bit loads)
+    long long blocks = (n / per + kThreads - 1) / kThreads;
+    // every CTA ends with one global atomic per bin on the same few addresses: cap the grid at two
+    // CTAs per SM and let each thread stream more labels instead
+    const long long cap = 2ll * num_sms();
+    if (blocks > cap) blocks = cap;
     int grid = 0;
     if (C + 2 <= 64) {
         const int smem = BinAcc<true>::smem_bytes(C + 2);

@@ -343,7 +343,9 @@ int tile_launch(const unsigned char* scene, int Cb, int H, int W, const int* til
     const int lut_bytes = p.use_lut ? Cb * 256 * 4 : 0;
     // grid: as many CTAs as stay resident; with private u16 histogram counters a warp must not
     // see more than 65535 label pixels per lane, which bounds the row items per warp
-    long long g = static_cast<long long>(num_sms()) * ((lut_bytes + (hist ? 16 * 1024 : 0)) > 24 * 1024 ? 4 : 8);
+    int ctas_per_sm = get_option(CVCS_OPT_TILE_CTAS);
+    if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = (lut_bytes + (hist ? 16 * 1024 : 0)) > 24 * 1024 ? 4 : 8;
+    long long g = static_cast<long long>(num_sms()) * ctas_per_sm;
     const long long warps_needed = p.n_rows;
     if (g * kWarps > warps_needed) g = (warps_needed + kWarps - 1) / kWarps;
     if (g > kMaxGrid) g = kMaxGrid;

@@ -92,7 +92,8 @@ enum cvcs_option {
     CVCS_OPT_TMA_WAIT_HINT = 2, /* 0: mbarrier waits pass a long suspend-time hint (default), 1: no hint */
     CVCS_OPT_TMA_VECP = 3,   /* NCHW, C <= 8: pixels per consumer thread (0 = default; f32: 2|4, bf16: 4|8) */
     CVCS_OPT_TMA_CTAS = 4,   /* CTAs per SM the TMA variant sizes its stages for (0 = default 2; 1..4)      */
-    CVCS_OPT_COUNT = 5
+    CVCS_OPT_TILE_CTAS = 5,  /* K5: CTAs per SM of the persistent grid (0 = default; 1..8)                  */
+    CVCS_OPT_COUNT = 6
 };
 int cvcs_set_option(int option, int value);
 
