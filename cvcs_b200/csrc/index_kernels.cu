@@ -161,6 +161,102 @@ __global__ void __launch_bounds__(kThreads) label_hist_kernel(const HistParams p
     }
 }
 
+// ---- K4, lean mode: Σ_i v_i w[y_i] without the histogram ------------------------------------------
+// When only the 'mean' divisor is wanted (the pre-pass in front of K1), counting is unnecessary: the
+// total weight is a plain sum of per-pixel table look-ups, with no read-modify-write chains.  u8 labels
+// index a 256-entry shared-memory table directly (0 for ignore_index and for anything >= C).
+// Per-thread fp32 partials of a few dozen terms -> fp64 block partials -> fixed-order fold by the last
+// CTA (run-to-run bit-stable).
+__global__ void __launch_bounds__(kThreads) weight_sum_kernel(const HistParams p) {
+    __shared__ float lut[256];
+    __shared__ double red[kWarps];
+    __shared__ unsigned int is_last;
+    const int C = p.C;
+    {
+        const int t = threadIdx.x;
+        lut[t] = (t < C && static_cast<long long>(t) != p.ignore_index) ? (p.weight ? p.weight[t] : 1.0f) : 0.f;
+    }
+    __syncthreads();
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+    if (!p.target_i64) {
+        const uint8_t* __restrict__ tgt = reinterpret_cast<const uint8_t*>(p.target);
+        const long long n16 = p.n / 16;
+        constexpr int U = 2;
+        for (long long base = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; base < n16; base += U * stride) {
+            Raw<16> r[U];
+            bool have[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                have[u] = base + u * stride < n16;
+                if (have[u]) r[u].load(tgt + 16 * (base + u * stride));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!have[u]) continue;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) a[k & 3] += lut[(r[u].word(k / 4) >> (8 * (k % 4))) & 0xff];
+            }
+        }
+        if (blockIdx.x == 0) {
+            const long long i = n16 * 16 + threadIdx.x;
+            if (i < p.n) a[0] += lut[tgt[i]];
+        }
+    } else {
+        const long long* __restrict__ tgt = reinterpret_cast<const long long*>(p.target);
+        const long long n2 = p.n / 2;
+        auto w_of = [&](long long v) { return (v >= 0 && v < C) ? lut[static_cast<int>(v)] : 0.f; };  // lut[ignore] == 0
+        constexpr int U = 4;
+        for (long long base = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; base < n2; base += U * stride) {
+            Raw<16> r[U];
+            bool have[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                have[u] = base + u * stride < n2;
+                if (have[u]) r[u].load(tgt + 2 * (base + u * stride));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!have[u]) continue;
+                a[u & 3] += w_of((static_cast<long long>(r[u].v.y) << 32) | r[u].v.x);
+                a[(u + 2) & 3] += w_of((static_cast<long long>(r[u].v.w) << 32) | r[u].v.z);
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (p.n & 1)) a[0] += w_of(tgt[p.n - 1]);
+    }
+    double s = static_cast<double>((a[0] + a[1]) + (a[2] + a[3]));
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) b += red[w];
+        p.ws->partial[blockIdx.x] = b;
+        __threadfence();
+        const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double tot = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kThreads) tot += __ldcg(&p.ws->partial[i]);
+    tot = warp_sum(tot);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) b += red[w];
+        p.tw_out[0] = b;
+        p.tw_out[1] = 1.0 / b;
+        p.ws->ticket = 0u;
+        __threadfence();
+    }
+}
+
 __global__ void total_weight_kernel(const unsigned long long* __restrict__ hist, const float* __restrict__ weight,
                                     int C, long long ignore_index, double* __restrict__ out) {
     // one warp; fixed order -> deterministic
@@ -428,6 +524,18 @@ int label_hist_launch(const void* target, int target_dtype, long long n, int C, 
     p.ignore_index = ignore_index;
     p.C = C;
     p.target_i64 = target_dtype == CVCS_I64;
+    if (!hist && tw_out && C <= 256) {
+        // lean mode: only the total weight is wanted -> no counting (see weight_sum_kernel)
+        const long long per_thread = p.target_i64 ? 8 : 32;
+        long long blocks = (n / per_thread + kThreads - 1) / kThreads;
+        const long long cap = 8ll * num_sms();
+        if (blocks > cap) blocks = cap;
+        if (blocks > kMaxGrid) blocks = kMaxGrid;
+        if (blocks < 1) blocks = 1;
+        weight_sum_kernel<<<static_cast<int>(blocks), kThreads, 0, stream>>>(p);
+        CVCS_CUDA_OK(cudaGetLastError());
+        return CVCS_OK;
+    }
     const int per = p.target_i64 ? 2 : 32;  // pixels per thread per step (u8: two 128-bit loads)
     long long blocks = (n / per + kThreads - 1) / kThreads;
     // every CTA ends with one global atomic per bin on the same few addresses: cap the grid at two
