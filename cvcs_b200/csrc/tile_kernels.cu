@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kThreads) stitch_kernel(const unsigned char* _
                                                           unsigned char* __restrict__ scene, int H, int W) {
     const long long per_tile = static_cast<long long>(ch) * cw;
     const long long total = per_tile * n_tiles;
-    const int oy = (th - ch) / 2, ox = (tw - cw) / 2;  // CenterCrop offsets (torchvision rounds (th-ch)/2.0 to even... see host)
+    const int oy = (th - ch) / 2, ox = (tw - cw) / 2;  // CenterCrop offsets (utils.py:146,154)
     for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * kThreads) {
         const int t = static_cast<int>(i / per_tile);
@@ -264,6 +264,34 @@ __global__ void __launch_bounds__(kThreads) stitch_kernel(const unsigned char* _
         const int sy = yx[2 * t] + y, sx = yx[2 * t + 1] + x;
         if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
         scene[static_cast<long long>(sy) * W + sx] = tiles[(static_cast<long long>(t) * th + oy + y) * tw + ox + x];
+    }
+}
+
+// 4 pixels per thread: crop width, crop offset, tile width and scene width multiples of 4 and aligned
+// bases; a group whose destination is not 4-aligned or leaves the scene falls back to byte stores.
+__global__ void __launch_bounds__(kThreads) stitch_x4_kernel(const unsigned char* __restrict__ tiles, int n_tiles, int th,
+                                                             int tw, const int* __restrict__ yx, int ch, int cw,
+                                                             unsigned char* __restrict__ scene, int H, int W) {
+    const int gpr = cw / 4;  // groups per cropped row
+    const long long per_tile = static_cast<long long>(ch) * gpr;
+    const long long total = per_tile * n_tiles;
+    const int oy = (th - ch) / 2, ox = (tw - cw) / 2;
+    for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * kThreads) {
+        const int t = static_cast<int>(i / per_tile);
+        const int r = static_cast<int>(i - t * per_tile);
+        const int y = r / gpr, x = (r - y * gpr) * 4;
+        const int sy = __ldg(yx + 2 * t) + y, sx = __ldg(yx + 2 * t + 1) + x;
+        if (sy < 0 || sy >= H) continue;
+        const unsigned int w = __ldcs(reinterpret_cast<const unsigned int*>(tiles + (static_cast<long long>(t) * th + oy + y) * tw + ox + x));
+        unsigned char* dst = scene + static_cast<long long>(sy) * W + sx;
+        if (sx >= 0 && sx + 3 < W && (sx & 3) == 0) {
+            *reinterpret_cast<unsigned int*>(dst) = w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (sx + k >= 0 && sx + k < W) dst[k] = static_cast<unsigned char>(w >> (8 * k));
+        }
     }
 }
 
@@ -285,6 +313,53 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const IT* __restrict__ m
             }
         }
         out[i] = static_cast<OT>(best_v);
+    }
+}
+
+// u8 maps, n_maps <= 8, n % 4 == 0, 4-byte aligned: each thread votes on 4 consecutive pixels; every map
+// is read exactly once (one 32-bit load per map) and the counting happens in registers.
+template <int NM>
+__global__ void __launch_bounds__(kThreads) vote_u8x4_kernel(const uint8_t* __restrict__ maps, long long n,
+                                                             uint8_t* __restrict__ out) {
+    const long long n4 = n / 4;
+    for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * kThreads) {
+        uint32_t w[NM];
+#pragma unroll
+        for (int a = 0; a < NM; ++a) w[a] = __ldcs(reinterpret_cast<const unsigned int*>(maps + a * n) + i);
+        uint32_t res = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int v[NM];
+#pragma unroll
+            for (int a = 0; a < NM; ++a) v[a] = static_cast<int>((w[a] >> (8 * k)) & 0xff);
+            int best_v = 0, best_c = 0;
+#pragma unroll
+            for (int a = 0; a < NM; ++a) {
+                int cnt = 0;
+#pragma unroll
+                for (int b = 0; b < NM; ++b) cnt += (v[b] == v[a]) ? 1 : 0;
+                // most frequent value; ties -> smallest value (torch.mode)
+                const bool take = cnt > best_c || (cnt == best_c && v[a] < best_v);
+                best_c = take ? cnt : best_c;
+                best_v = take ? v[a] : best_v;
+            }
+            res |= static_cast<uint32_t>(best_v) << (8 * k);
+        }
+        __stcs(reinterpret_cast<unsigned int*>(out) + i, res);
+    }
+}
+
+template <int NM>
+bool try_vote_u8x4(const void* maps, int n_maps, long long n, void* out, cudaStream_t stream, int grid) {
+    if constexpr (NM > 8) {
+        return false;
+    } else {
+        if (n_maps == NM) {
+            vote_u8x4_kernel<NM><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const uint8_t*>(maps), n, reinterpret_cast<uint8_t*>(out));
+            return true;
+        }
+        return try_vote_u8x4<NM + 1>(maps, n_maps, n, out, stream, grid);
     }
 }
 
@@ -415,7 +490,11 @@ int stitch_launch(const unsigned char* tiles, int n_tiles, int th, int tw, const
     CVCS_REQUIRE(n_tiles >= 0 && th > 0 && tw > 0 && ch > 0 && cw > 0 && ch <= th && cw <= tw && H > 0 && W > 0, "cvcs_stitch: bad shape");
     if (n_tiles == 0) return CVCS_OK;
     const long long total = static_cast<long long>(n_tiles) * ch * cw;
-    stitch_kernel<<<simple_grid(total), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W);
+    const int ox = (tw - cw) / 2;
+    const bool x4 = cw % 4 == 0 && tw % 4 == 0 && ox % 4 == 0 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(tiles) & 3u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(scene) & 3u) == 0;
+    if (x4) stitch_x4_kernel<<<simple_grid(total / 4), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W);
+    else stitch_kernel<<<simple_grid(total), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W);
     CVCS_CUDA_OK(cudaGetLastError());
     return CVCS_OK;
 }
@@ -427,6 +506,12 @@ int vote_launch(const void* maps, int dtype, int n_maps, long long n, int C, voi
     CVCS_REQUIRE(dtype == CVCS_U8 || dtype == CVCS_I64, "cvcs_vote: dtype tag %d", dtype);
     CVCS_REQUIRE(out_dtype == CVCS_U8 || out_dtype == CVCS_I64, "cvcs_vote: out dtype tag %d", out_dtype);
     const int g = simple_grid(n);
+    auto al4 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 3u) == 0; };
+    if (dtype == CVCS_U8 && out_dtype == CVCS_U8 && n_maps <= 8 && n % 4 == 0 && al4(maps) && al4(out) &&
+        try_vote_u8x4<1>(maps, n_maps, n, out, stream, simple_grid(n / 4))) {
+        CVCS_CUDA_OK(cudaGetLastError());
+        return CVCS_OK;
+    }
     if (dtype == CVCS_U8 && out_dtype == CVCS_U8)
         vote_kernel<<<g, kThreads, 0, stream>>>(reinterpret_cast<const uint8_t*>(maps), n_maps, n, reinterpret_cast<uint8_t*>(out));
     else if (dtype == CVCS_U8)

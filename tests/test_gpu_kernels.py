@@ -214,3 +214,28 @@ def test_tile_argmax_stitch_roundtrip():
     back = ops.stitch(tiles[:, 0].contiguous(), yx, (H, W))
     assert torch.equal(back[:rows * p, :cols * p], lab[:rows * p, :cols * p])
     assert int(back[rows * p:].sum()) == 0 and int(back[:, cols * p:].sum()) == 0
+
+
+@pytest.mark.parametrize("n_maps", [1, 2, 3, 5, 8, 9])
+@pytest.mark.parametrize("n", [4096, 4099])
+def test_vote_vector_and_scalar_paths(n_maps, n):
+    """Majority vote (torch.mode tie rule) on u8 maps: the 4-pixel register path (n % 4 == 0, <= 8 maps) and
+    the generic path agree with the oracle."""
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(n_maps * 31 + n)
+    maps = torch.randint(0, 6, (n_maps, n), generator=g, dtype=torch.uint8)
+    ref = c_oracle.vote(maps.numpy().astype(np.int64))
+    assert np.array_equal(ops.vote(maps.to(DEV)).cpu().numpy().astype(np.int64), ref)
+    assert np.array_equal(ops.vote(maps.long().to(DEV)).cpu().numpy(), ref)
+    assert np.array_equal(torch.mode(maps.long(), dim=0).values.numpy(), ref)     # the oracle is torch.mode (utils.py:506)
+
+
+def test_stitch_vector_path_with_center_crop():
+    """Border-corrected stitching (CenterCrop of the padded tile, utils.py:146,154): 4-pixel path vs oracle."""
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    n, th, ch, H, W = 6, 32, 24, 80, 104
+    tiles = torch.randint(0, 16, (n, th, th), generator=g, dtype=torch.uint8)
+    yx = torch.tensor([[0, 0], [0, 24], [24, 48], [56, 80], [-8, 100], [72, -4]], dtype=torch.int32)
+    out = ops.stitch(tiles.to(DEV), yx.to(DEV), (H, W), crop_hw=(ch, ch))
+    assert np.array_equal(out.cpu().numpy(), c_oracle.stitch(tiles.numpy(), yx.numpy(), H, W, crop=(ch, ch)))
