@@ -302,6 +302,7 @@ def main():
     ap.add_argument("--ctas", type=int, default=0, help="A/B: CTAs per SM the TMA variant sizes its stages for")
     ap.add_argument("--vecp", type=int, default=0, help="A/B: pixels per consumer thread of the TMA variant (f32: 2|4, bf16: 4|8)")
     ap.add_argument("--label-dtype", default="u8", choices=["u8", "i64"])
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"], help="logits memory format (nhwc = torch channels_last)")
     ap.add_argument("--no-grad", action="store_true", help="forward/eval only (no dlogits)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-copy-ref", action="store_true", help="skip the same-size torch copy reference measurement")
@@ -350,73 +351,109 @@ def main():
     sets, weight = synth_inputs(torch, wl, dev, seed=1234 + rank, n_sets=n_sets)
     if args.label_dtype == "i64":
         sets = [(x, t.long()) for x, t in sets]
+    if args.layout == "nhwc":
+        sets = [(x.contiguous(memory_format=torch.channels_last), t) for x, t in sets]
     dl = [torch.empty_like(x) for x, _ in sets] if grad else [None] * n_sets
     am = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in sets]
     confmat = torch.zeros((C, C), dtype=torch.int64, device=dev)
     loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
     sums = torch.zeros(3, dtype=torch.float64, device=dev)
-    tw = torch.zeros(2, dtype=torch.float64, device=dev)
-    hist = torch.zeros(C + 2, dtype=torch.int64, device=dev)
     ii = wl["ignore_index"]
     data_dependent_tw = wl["weighted"] or (0 <= ii <= 255) or args.label_dtype == "i64"
+    prepass_on = grad and data_dependent_tw
+    # K4 pre-pass (Σ v·w[y] must be known before the first dlogit is written) runs ONE STEP AHEAD on its own
+    # stream: the labels of the next batch are known while the current K1 runs (as in a training loop with a
+    # prefetching loader), so the pre-pass — and at N > 1 its label-histogram all-reduce — overlaps K1.
+    pre = torch.cuda.Stream(device=dev) if prepass_on else None
+    tws = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(n_sets)]
+    hists = [torch.zeros(C + 2, dtype=torch.int64, device=dev) for _ in range(n_sets)]
+    pre_ready = [None] * n_sets      # event on `pre`: tws[j] holds this step's total weight
+    k1_done = [None] * n_sets        # event on the main stream: the K1 that read tws[j] has run
+    issued = {"upto": -1}
     side = torch.cuda.Stream(device=dev) if world > 1 else None
+    sums_sets = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(n_sets)]
+    sums = sums_sets[0]
     sums_comm = torch.zeros(3, dtype=torch.float64, device=dev)
     launches = {"n": 0}
     k1_events = []
 
-    def step(i, timed):
-        x, t = sets[i % n_sets]
+    def prepass(i):
+        j = i % n_sets
+        _, t = sets[j]
+        if k1_done[j] is not None:
+            pre.wait_event(k1_done[j])
+        with torch.cuda.stream(pre):
+            if world > 1:
+                hists[j].zero_()
+                ops.label_hist(t, C, ii, hist=hists[j])
+                dist.all_reduce(hists[j])                       # global Σw: results equal the 1-process run
+                ops.total_weight(hists[j], weight, C, ii, out=tws[j])
+                launches["n"] += 2
+            else:
+                ops.label_hist(t, C, ii, weight=weight, total_weight_out=tws[j])
+                launches["n"] += 1
+            ev = torch.cuda.Event()
+            ev.record(pre)
+        pre_ready[j] = ev
+        issued["upto"] = i
+
+    def step(i, timed, last=False):
+        j = i % n_sets
+        x, t = sets[j]
         inv, inv_dev = 0.0, None
         if grad:
-            if data_dependent_tw:
-                # K4 pre-pass: Σ v·w[y] must be known before the first dlogit is written
-                if world > 1:
-                    hist.zero_()
-                    ops.label_hist(t, C, ii, hist=hist)
-                    dist.all_reduce(hist)                       # global Σw: results equal the 1-process run
-                    ops.total_weight(hist, weight, C, ii, out=tw)
-                    launches["n"] += 2
-                else:
-                    ops.label_hist(t, C, ii, weight=weight, total_weight_out=tw)
-                    launches["n"] += 1
-                inv_dev = tw[1:]
+            if prepass_on:
+                if issued["upto"] < i:
+                    prepass(i)
+                torch.cuda.current_stream(dev).wait_event(pre_ready[j])
+                inv_dev = tws[j][1:]
             else:
                 inv = 1.0 / float(px_per_gpu * world)           # nothing can be ignored: Σw = global pixel count
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         ops.ce_fused(x, t, weight, ii, want_grad=grad, inv_total_weight=inv, inv_total_weight_dev=inv_dev,
-                     dlogits=dl[i % n_sets], argmax=am[i % n_sets], confmat=confmat, loss_sums=sums, loss_out=loss_out)
+                     dlogits=dl[j], argmax=am[j], confmat=confmat, loss_sums=sums_sets[j], loss_out=loss_out)
         launches["n"] += 1
         if timed:
             e1.record()
             k1_events.append((e0, e1))
+        if prepass_on:
+            k1_done[j] = torch.cuda.Event()
+            k1_done[j].record()
+            if not last:
+                prepass(i + 1)
         if world > 1:
             # global loss of this step: f64[3] all-reduce on a side stream, overlapped with the next K1
             ev = torch.cuda.Event()
             ev.record()
             side.wait_event(ev)
             with torch.cuda.stream(side):
-                sums_comm.copy_(sums)
+                sums_comm.copy_(sums_sets[j])
                 dist.all_reduce(sums_comm)
 
     def fence():
+        if pre is not None:
+            torch.cuda.current_stream(dev).wait_stream(pre)
         if world > 1:
             torch.cuda.current_stream(dev).wait_stream(side)
             dist.barrier()
         torch.cuda.synchronize(dev)
 
     for i in range(args.warmup):
-        step(i, False)
+        step(i, False, last=(i == args.warmup - 1))
     fence()
     confmat.zero_()
     launches["n"] = 0
+    issued["upto"] = -1
     sampler = ClockSampler(local)
     sampler.start()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(args.steps):
-        step(i, True)
+        step(i, True, last=(i == args.steps - 1))
+    if pre is not None:
+        torch.cuda.current_stream(dev).wait_stream(pre)
     if world > 1:
         torch.cuda.current_stream(dev).wait_stream(side)
         dist.all_reduce(confmat)                                # one C*C all-reduce per pass
@@ -504,11 +541,11 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": wl["dtype"], "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "per_gpu_batch": B, "classes": C,
-                       "tile": [H, W], "labels": args.label_dtype + " (blocky 32x32)", "grad": grad,
+                       "tile": [H, W], "labels": args.label_dtype + " (blocky 32x32)", "grad": grad, "layout": args.layout,
                        "l2": f"inputs larger than L2: {n_sets} rotating sets of {px_per_gpu * C * esize * (2 if grad else 1) / 1e6:.0f} MB",
                        "parallelism": f"dp{world}: tiles sharded per GPU; f64[3] loss all-reduce per step (side stream) + "
                                       "one CxC confusion all-reduce per pass" if world > 1 else "single GPU",
-                       "k4_prepass": bool(grad and data_dependent_tw), "path": args.path},
+                       "k4_prepass": "one step ahead on a side stream (overlaps K1)" if prepass_on else False, "path": args.path},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
             "clocks": sampler.summary(),
             "check": {"confusion_total": total_cm, "loss": float(loss_out.item())},

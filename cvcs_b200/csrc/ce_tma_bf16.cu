@@ -15,7 +15,10 @@ int ce_tma_launch_bf16(const CeParams& p, int layout, cudaStream_t stream, bool*
         if (p.C <= 16) return tma::dispatch<__nv_bfloat16, 4, false, 9, 16>(p, stream, handled);
         return tma::dispatch<__nv_bfloat16, 2, false, 17, kMaxRegC>(p, stream, handled);
     }
-    return tma::dispatch<__nv_bfloat16, 8, true, 2, 12>(p, stream, handled);
+    if (p.C <= 12) return tma::dispatch<__nv_bfloat16, 8, true, 2, 12>(p, stream, handled);
+    if (p.C % 4 == 0) return tma::dispatch<__nv_bfloat16, 2, true, 13, kMaxRegC>(p, stream, handled);   // 16, 20
+    if (p.C % 2 == 0) return tma::dispatch<__nv_bfloat16, 4, true, 13, kMaxRegC>(p, stream, handled);   // 14, 18
+    return CVCS_OK;  // odd C > 12: generic variant
 }
 
 }  // namespace cvcs

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
                 // ---- math.  fp32: one pixel at a time; bf16 NCHW: two pixels at a time, because a 32-bit
                 // word of a class plane holds the pixel pair (2j, 2j+1) and both gradients are packed with one
                 // cvt.rn.bf16x2 (the compiler interleaves the unrolled groups either way)
-                constexpr int PP = (ES == 2 && !NHWC && VECP % 2 == 0) ? 2 : 1;
+                constexpr int PP = (ES == 2 && VECP % 2 == 0) ? 2 : 1;
                 int amax[VECP];
                 float gfix[VECP];     // gradient of the target class, patched into the stage afterwards
                 float step_l = 0.f, step_w = 0.f;
@@ -418,9 +418,13 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
                         for (int c = 0; c < C; ++c) {
                             if constexpr (ES == 4) {
                                 raw[ridx(c, k0)] = __float_as_uint(x[0][c] * r[0]);
-                            } else if constexpr (PP == 2) {
+                            } else if constexpr (PP == 2 && !NHWC) {
                                 raw[ridx(c, k0) >> 1] = pack_bf16(x[0][c] * r[0], x[PP - 1][c] * r[PP - 1]);
-                            } else {  // bf16 NHWC: RNE, merged into the half of the word this element owns
+                            } else if constexpr (PP == 2 && NHWC) {
+                                // the pixel pair's 2C values are C consecutive words: word c holds flat elements 2c, 2c+1
+                                auto flat = [&](int e) { return e < C ? x[0][e < C ? e : 0] * r[0] : x[PP - 1][e < C ? 0 : e - C] * r[PP - 1]; };
+                                raw[(ridx(0, k0) >> 1) + c] = pack_bf16(flat(2 * c), flat(2 * c + 1));
+                            } else {  // bf16, one pixel per thread: RNE, merged into the half of the word this element owns
                                 const int e = ridx(c, k0);
                                 const uint32_t h = pack_bf16(x[0][c] * r[0], 0.f) & 0xffffu;
                                 raw[e >> 1] = (e & 1) ? ((raw[e >> 1] & 0x0000ffffu) | (h << 16)) : ((raw[e >> 1] & 0xffff0000u) | h);
@@ -539,15 +543,23 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     return CVCS_OK;
 }
 
+// NHWC: a thread's span of VECP pixels x C classes must be whole 16-byte vectors
+template <typename T, int C, int VECP, bool NHWC>
+constexpr bool span_ok() {
+    return !NHWC || (VECP * C * static_cast<int>(sizeof(T))) % 16 == 0;
+}
+
 template <typename T, int VECP, bool NHWC, int CLO, int CHI, int CC = CLO>
 int dispatch(const CeParams& p, cudaStream_t stream, bool* handled) {
     if constexpr (CC > CHI) {
         *handled = false;
         return CVCS_OK;
     } else {
-        if (p.C == CC) {
-            *handled = true;
-            return launch<T, CC, VECP, NHWC>(p, stream, handled);
+        if constexpr (span_ok<T, CC, VECP, NHWC>()) {
+            if (p.C == CC) {
+                *handled = true;
+                return launch<T, CC, VECP, NHWC>(p, stream, handled);
+            }
         }
         return dispatch<T, VECP, NHWC, CLO, CHI, CC + 1>(p, stream, handled);
     }

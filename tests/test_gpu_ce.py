@@ -101,7 +101,7 @@ def test_golden_cases_fp32(golden, lib, name, path):
 
 @pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
 @pytest.mark.parametrize("label_dtype", [torch.uint8, torch.int64])
-@pytest.mark.parametrize("C", [2, 5, 7, 8, 12, 16, 20, 21, 33])
+@pytest.mark.parametrize("C", [2, 5, 7, 8, 12, 14, 16, 18, 20, 21, 33])
 def test_random_fp32(lib, layout, label_dtype, C):
     g = torch.Generator().manual_seed(C)
     B, H, W = 3, 48, 80
@@ -124,7 +124,7 @@ def test_random_fp32(lib, layout, label_dtype, C):
 
 @pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
 @pytest.mark.parametrize("path", ["auto", "direct", "generic"])
-@pytest.mark.parametrize("C", [7, 12, 13, 20])
+@pytest.mark.parametrize("C", [7, 12, 13, 14, 16, 18, 20])
 def test_random_bf16(lib, layout, path, C):
     """cfg3: bf16 logits, class weights, ignore_index=255.  Oracle = fp32 CE on the same bf16 values."""
     lib.set_option(lib.OPT_CE_PATH, PATHS[path])
@@ -192,16 +192,35 @@ def test_ragged_shapes(lib, shape):
         check_against(loss, grad, am, cm, logits, target, None, 0, F32_TOL)
 
 
-@pytest.mark.parametrize("stages", [2, 3])
-def test_tma_pipeline_depths(lib, stages):
+@pytest.mark.parametrize("grad", [True, False])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("ctas,stages,vecp_small", [(0, 0, False), (1, 2, False), (1, 4, True), (2, 2, True), (2, 3, False), (3, 3, True)])
+def test_tma_pipeline_geometries(lib, ctas, stages, vecp_small, dtype, grad):
+    """Every pipeline geometry the tuning knobs can select (CTAs/SM x stages x pixels per thread) gives the
+    same results: the knobs only move bytes in flight."""
     lib.set_option(lib.OPT_CE_PATH, PATHS["tma"])
     lib.set_option(lib.OPT_TMA_STAGES, stages)
-    g = torch.Generator().manual_seed(7)
-    B, C, H, W = 4, 7, 256, 256                                  # 256 chunks of 1024 px
-    logits = torch.randn(B, C, H, W, generator=g).numpy()
-    target = torch.randint(0, C, (B, H, W), generator=g).numpy().astype(np.int64)
-    loss, sums, grad, am, cm = run_k1(logits, target, None, 0)
-    check_against(loss, grad, am, cm, logits, target, None, 0, F32_TOL)
+    lib.set_option(lib.OPT_TMA_CTAS, ctas)
+    lib.set_option(lib.OPT_TMA_VECP, (2 if dtype == torch.float32 else 4) if vecp_small else (4 if dtype == torch.float32 else 8))
+    try:
+        g = torch.Generator().manual_seed(7)
+        B, C, H, W = 4, 7, 256, 256                              # 256 chunks of 1024 px
+        logits = (torch.randn(B, C, H, W, generator=g) * 3).to(dtype).float().numpy()
+        target = torch.randint(0, C, (B, H, W), generator=g).numpy().astype(np.int64)
+        target[0, :40] = 0
+        w = (torch.rand(C, generator=g) + 0.5).numpy()
+        loss, sums, grad_out, am, cm = run_k1(logits, target, w, 0, dtype=dtype, want_grad=grad)
+        tol = F32_TOL if dtype == torch.float32 else BF16_TOL
+        if grad:
+            check_against(loss, grad_out, am, cm, logits, target, w, 0, tol)
+        else:
+            l_ref, _, _ = c_oracle.cross_entropy(logits, target, w, 0, want_grad=False)
+            am_ref = c_oracle.argmax(logits)
+            assert grad_out is None and abs(loss - l_ref) <= tol * abs(l_ref)
+            assert np.array_equal(am, am_ref) and np.array_equal(cm, c_oracle.confmat(am_ref, target, C, 0)[0])
+    finally:
+        lib.set_option(lib.OPT_TMA_CTAS, 0)
+        lib.set_option(lib.OPT_TMA_VECP, 0)
 
 
 def test_run_to_run_bit_stable(lib):
