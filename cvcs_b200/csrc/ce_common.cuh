@@ -268,6 +268,7 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
         }
         p.ws->bad = 0ull;
         p.ws->ticket = 0u;
+        p.ws->next_chunk = 0u;
         __threadfence();
     }
 }

@@ -1,17 +1,20 @@
 // ce_tma_impl.cuh — K1, TMA-staged variant (the primary path).
 //
-// A persistent, warp-specialised CTA per resident slot:
-//   * one producer lane drives the bulk-copy engine: `cp.async.bulk` (TMA, 1-D) pulls a chunk of
+// A persistent, warp-specialised CTA (256 consumer threads + a loader warp + a storer warp):
+//   * the loader lane drives the bulk-copy engine: `cp.async.bulk` (TMA, 1-D) pulls a chunk of
 //     P pixels — C class planes of P·esize bytes each for NCHW, or one contiguous P·C·esize span
-//     for NHWC — plus the chunk's labels into a shared-memory stage, completing on an mbarrier;
-//     finished stages are pushed back to HBM with `cp.async.bulk.global.shared::cta`.
-//   * 256 consumer threads wait on the stage's mbarrier, read their VECP pixels from shared
-//     memory with conflict-free vector loads, run the per-pixel softmax-CE / gradient / argmax
-//     arithmetic in registers, overwrite the logits with the gradients IN PLACE, fence to the
-//     async proxy and arrive on the stage's "done" mbarrier.
-// Bytes in flight are set by the number of stages, not by registers or occupancy, so the
-// memory pipeline stays full while each logit is read once and each gradient written once.
-// A CTA handles chunks blockIdx.x, blockIdx.x + gridDim.x, ... (static round-robin).
+//     for NHWC — plus the chunk's labels into a shared-memory stage, completing on the stage's
+//     `full` mbarrier;
+//   * 256 consumer threads wait on `full`, read their VECP pixels from shared memory with
+//     conflict-free vector loads, run the per-pixel softmax-CE / gradient / argmax arithmetic in
+//     registers, overwrite the logits with the gradients IN PLACE, fence to the async proxy and
+//     arrive on the stage's `done` mbarrier;
+//   * the storer lane waits on `done`, pushes the stage back to HBM with
+//     `cp.async.bulk.global.shared::cta` and arrives on the stage's `free` mbarrier as soon as the
+//     store has finished reading shared memory, which is what the loader waits for before refilling.
+// Bytes in flight are set by the number of stages, not by registers or occupancy; each logit is
+// read once and each gradient written once.  The geometry (stages per CTA, CTAs per SM) is chosen
+// from measurements in launch().  A CTA handles chunks blockIdx.x, blockIdx.x + gridDim.x, ...
 //
 // Requirements checked by the launcher: 16-byte aligned base pointers, H·W % 16 == 0 (NCHW)
 // or B·H·W % 16 == 0 (NHWC) so that every bulk copy is a multiple of 16 bytes.
@@ -28,7 +31,7 @@ constexpr int kConsumerBar = 1;  // named barrier of the 256 consumer threads
 
 struct Geom {
     int stages;
-    int wait_hint;     // 1: consumers' and producer's mbarrier waits pass a long suspend-time hint
+    int wait_hint;     // 1: mbarrier waits pass a long suspend-time hint
     int stage_bytes;   // logits + labels, multiple of 128
     int label_off;     // offset of the labels inside a stage
     int hist_off;      // offset of the bin accumulators in dynamic smem
@@ -109,56 +112,39 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- chunk addressing -----------------------------------------------------------------------
-// A CTA walks chunks q = blockIdx.x, blockIdx.x + gridDim.x, ...  For NCHW a chunk is P pixels of
-// one image (b, k); the walker advances (b, k) incrementally so the loops hold no integer division.
+// Chunks are claimed dynamically: a CTA starts with chunk blockIdx.x and its loader then draws
+// gridDim.x + atomicAdd(next_chunk) — SMs that run faster (nearer L2 slices, fewer DRAM conflicts)
+// simply take more chunks, so all CTAs finish within one chunk of each other.  The loader publishes
+// the chunk's coordinates in a per-stage descriptor; consumers and storer read them after the
+// stage's barrier, so only one thread per chunk does the index arithmetic.
 struct Chunk {
     long long pix0;    // global pixel index of the chunk's first pixel (b*hw + k*P for NCHW)
     long long elem0;   // NCHW: element offset of plane 0 (b*C*hw + k*P); NHWC: pix0 * C
-    int n;             // valid pixels in the chunk
+    int n;             // valid pixels in the chunk; < 0: no more chunks (sentinel)
+    int pad;
 };
 
 template <int C, int P, bool NHWC>
-struct ChunkWalker {
-    unsigned int b, k, step_b, step_k, ipi;
-    long long q;
-    __device__ __forceinline__ void init(const CeParams& p) {
-        q = blockIdx.x;
-        if constexpr (!NHWC) {
-            ipi = p.items_per_image;
-            b = blockIdx.x / ipi;
-            k = blockIdx.x - b * ipi;
-            step_b = gridDim.x / ipi;
-            step_k = gridDim.x - step_b * ipi;
-        }
+__device__ __forceinline__ Chunk chunk_of(const CeParams& p, long long q) {
+    Chunk ck;
+    ck.pad = 0;
+    if constexpr (NHWC) {
+        ck.pix0 = q * P;
+        ck.elem0 = ck.pix0 * C;
+        const long long rem = p.n_pixels - ck.pix0;
+        ck.n = rem < P ? static_cast<int>(rem) : P;
+    } else {
+        const unsigned int q32 = static_cast<unsigned int>(q);
+        const unsigned int b = q32 / p.items_per_image;
+        const unsigned int k = q32 - b * p.items_per_image;
+        const long long in_img = static_cast<long long>(k) * P;
+        ck.pix0 = static_cast<long long>(b) * p.hw + in_img;
+        ck.elem0 = static_cast<long long>(b) * C * p.hw + in_img;
+        const long long rem = p.hw - in_img;
+        ck.n = rem < P ? static_cast<int>(rem) : P;
     }
-    __device__ __forceinline__ Chunk get(const CeParams& p) const {
-        Chunk ck;
-        if constexpr (NHWC) {
-            ck.pix0 = q * P;
-            ck.elem0 = ck.pix0 * C;
-            const long long rem = p.n_pixels - ck.pix0;
-            ck.n = rem < P ? static_cast<int>(rem) : P;
-        } else {
-            const long long in_img = static_cast<long long>(k) * P;
-            ck.pix0 = static_cast<long long>(b) * p.hw + in_img;
-            ck.elem0 = static_cast<long long>(b) * C * p.hw + in_img;
-            const long long rem = p.hw - in_img;
-            ck.n = rem < P ? static_cast<int>(rem) : P;
-        }
-        return ck;
-    }
-    __device__ __forceinline__ void next() {
-        q += gridDim.x;
-        if constexpr (!NHWC) {
-            k += step_k;
-            b += step_b;
-            if (k >= ipi) {
-                k -= ipi;
-                ++b;
-            }
-        }
-    }
-};
+    return ck;
+}
 
 // ring position: stage index + phase parity, advanced without a modulo
 struct Ring {
@@ -190,8 +176,13 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ float wsm[C];
     __shared__ __align__(8) unsigned long long bars[3 * kMaxStages];  // full[S], done[S], free[S]
+    __shared__ __align__(16) Chunk desc[kMaxStages];                   // what each stage currently holds
 
     const int tid = threadIdx.x;
+#ifdef CVCS_X_TIMING
+    unsigned long long t_start = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
     constexpr bool do_grad = GRAD;
     const bool do_arg = p.argmax != nullptr;
     const bool do_conf = p.confmat != nullptr;
@@ -213,7 +204,6 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
     __syncthreads();
 
     const long long n_chunks = p.n_items;
-    const long long mine = (n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     double lsum = 0.0, wsum = 0.0;
     unsigned int bad = 0;
@@ -232,21 +222,26 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
         };
         if (tid == kThreads) {
             // ---- loader
-            ChunkWalker<C, P, NHWC> ld;
-            ld.init(p);
             Ring ring{0, 0u};
-            for (long long i = 0; i < mine; ++i) {
+            long long q = blockIdx.x;
+            for (long long i = 0;; ++i) {
                 if (i >= S) {
                     // the stage's previous occupant: stored away (grad) / consumed (forward only)
                     const uint32_t prev = ring.phase ^ 1u;
                     if constexpr (do_grad) wait(bar0 + 8 * (2 * kMaxStages + ring.s), prev);
                     else wait(bar0 + 8 * (kMaxStages + ring.s), prev);
                 }
-                const Chunk ck = ld.get(p);
-                const uint32_t dst = stage0 + ring.s * g.stage_bytes;
                 const uint32_t bar = bar0 + 8 * ring.s;
+                if (q >= n_chunks) {          // nothing left: tell consumers and storer, then leave
+                    desc[ring.s].n = -1;
+                    mbar_arrive(bar);
+                    break;
+                }
+                const Chunk ck = chunk_of<C, P, NHWC>(p, q);
+                desc[ring.s] = ck;
+                const uint32_t dst = stage0 + ring.s * g.stage_bytes;
                 const uint32_t lbytes = static_cast<uint32_t>(ck.n) * tsize;
-                mbar_expect_tx(bar, static_cast<uint32_t>(ck.n) * C * ES + lbytes);
+                mbar_expect_tx(bar, static_cast<uint32_t>(ck.n) * C * ES + lbytes);   // release: publishes desc
                 if constexpr (NHWC) {
                     bulk_g2s(dst, logits + ck.elem0, static_cast<uint32_t>(ck.n) * C * ES, bar);
                 } else {
@@ -255,17 +250,16 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
                         bulk_g2s(dst + c * P * ES, logits + ck.elem0 + c * p.hw, static_cast<uint32_t>(ck.n) * ES, bar);
                 }
                 bulk_g2s(dst + g.label_off, target + ck.pix0 * tsize, lbytes, bar);
-                ld.next();
+                // claim the next chunk now: the atomic's round trip overlaps the wait for the next stage
+                q = static_cast<long long>(gridDim.x) + atomicAdd(&p.ws->next_chunk, 1u);
                 ring.next(S);
             }
         } else if (do_grad && tid == kThreads + 32) {
             // ---- storer: up to two bulk stores in flight; a stage is handed back to the loader as soon
             // as its store has finished reading shared memory — before blocking on the next `done`
-            ChunkWalker<C, P, NHWC> st;
-            st.init(p);
             Ring ring{0, 0u};
             int pending = -1;  // stage whose store has been issued but not yet waited for
-            for (long long i = 0; i < mine; ++i) {
+            for (;;) {
                 const uint32_t done = bar0 + 8 * (kMaxStages + ring.s);
                 if (pending >= 0 && !mbar_test(done, ring.phase)) {
                     bulk_wait_read<0>();
@@ -273,7 +267,8 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
                     pending = -1;
                 }
                 wait(done, ring.phase);
-                const Chunk ck = st.get(p);
+                const Chunk ck = desc[ring.s];
+                if (ck.n < 0) break;
                 const uint32_t src = stage0 + ring.s * g.stage_bytes;
                 if constexpr (NHWC) {
                     bulk_s2g(dlogits + ck.elem0, src, static_cast<uint32_t>(ck.n) * C * ES);
@@ -288,7 +283,6 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
                     mbar_arrive(bar0 + 8 * (2 * kMaxStages + pending));    // -> the loader may refill that stage
                 }
                 pending = ring.s;
-                st.next();
                 ring.next(S);
             }
             bulk_wait_all();
@@ -300,16 +294,18 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
         const float inv_tw = do_grad ? static_cast<float>(p.inv_tw_dev ? *p.inv_tw_dev : p.inv_tw) : 0.f;
         const int ign8 = ignore_as_int_u8(p.ignore_index);
         unsigned int since_flush = 0;
-        ChunkWalker<C, P, NHWC> walk;
-        walk.init(p);
         Ring ring{0, 0u};
         const int pix_t0 = tid * VECP;  // this thread's first pixel inside a chunk
 
-        for (long long i = 0; i < mine; ++i) {
-            const Chunk ck = walk.get(p);
+        for (;;) {
             unsigned char* stage = smem + g.stage_off + ring.s * g.stage_bytes;
             if (g.wait_hint) mbar_wait<true>(bar0 + 8 * ring.s, ring.phase);
             else mbar_wait<false>(bar0 + 8 * ring.s, ring.phase);
+            const Chunk ck = desc[ring.s];
+            if (ck.n < 0) {                   // sentinel: pass it on to the storer and leave
+                mbar_arrive(bar0 + 8 * (kMaxStages + ring.s));
+                break;
+            }
             if (pix_t0 < ck.n) {
                 // element index of (class c, pixel j of the chunk) inside the stage
                 auto eidx = [&](int c, int j) { return NHWC ? j * C + c : c * P + j; };
@@ -476,11 +472,19 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
                     since_flush = 0;
                 }
             }
-            walk.next();
             ring.next(S);
         }
         if (do_conf) conf.flush(p.confmat);
     }
+#ifdef CVCS_X_TIMING
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        p.ws->hist[blockIdx.x] = t_end;          // experiment build only: the caller re-zeroes the workspace
+        p.ws->hist[512 + blockIdx.x] = t_start;
+    }
+#endif
     finish_loss<kBlock / 32>(p, lsum, wsum, bad);
 }
 

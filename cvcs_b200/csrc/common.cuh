@@ -34,7 +34,7 @@ constexpr int kMaxHistBins = 1032;  // C <= 1024 plus {ignored, out-of-bounds}
 constexpr int kMaxGrid = 4096;  // upper bound on persistent grid size (148 SMs x <=16 CTAs, rounded)
 struct Workspace {
     unsigned int ticket;          // last-block election counter
-    unsigned int pad0;
+    unsigned int next_chunk;      // K1 (TMA variant): dynamic chunk claim counter
     unsigned long long bad;       // out-of-bounds label counter
     unsigned long long pad1[6];
     double partial[2 * kMaxGrid]; // per-block {Σ w·nll, Σ w}
