@@ -104,6 +104,8 @@ class FusedCrossEntropyLoss(nn.Module):
         self.last_argmax: Optional[torch.Tensor] = None
         self.last_sums: Optional[torch.Tensor] = None  # f64[3] {Σ w·nll, Σ w, #out-of-bounds}
         self._w32: Optional[torch.Tensor] = None
+        self._prefetched = None   # (target tensor, num_classes, f64[2] total weight, ready event)
+        self._side: Optional[torch.cuda.Stream] = None
 
     # -- helpers -------------------------------------------------------------------------------------
     def _weight_f32(self, dev: torch.device) -> Optional[torch.Tensor]:
@@ -112,6 +114,26 @@ class FusedCrossEntropyLoss(nn.Module):
         if self._w32 is None or self._w32.device != dev:
             self._w32 = self.weight.to(device=dev, dtype=torch.float32).contiguous()
         return self._w32
+
+    def prefetch_total_weight(self, target: torch.Tensor, num_classes: int) -> None:
+        """Optional: start the label pre-pass (K4, Σ v·w[y]) for ``target`` on a side stream NOW — e.g. right
+        after the batch is loaded, while the model's forward pass runs — so that the next ``forward`` with this
+        same target tensor finds the 'mean' divisor ready instead of computing it in front of the fused kernel."""
+        if not target.is_cuda or target.dtype not in (torch.int64, torch.uint8):
+            return
+        dev = target.device
+        t = target.reshape(target.shape[0], -1, 1) if target.dim() != 3 else target
+        if self._side is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        self._side.wait_stream(torch.cuda.current_stream(dev))     # the labels must have been produced
+        tw = torch.empty(2, dtype=torch.float64, device=dev)
+        with torch.cuda.stream(self._side):
+            ops.label_hist(t.contiguous(), num_classes, self.ignore_index, hist=None, weight=self._weight_f32(dev),
+                           total_weight_out=tw)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        tw.record_stream(self._side)
+        self._prefetched = (target, num_classes, tw, ev)
 
     def _run(self, logits: torch.Tensor, target: torch.Tensor, want_grad: bool):
         if not logits.is_cuda:
@@ -132,6 +154,11 @@ class FusedCrossEntropyLoss(nn.Module):
         if want_grad:
             if w is None and t.dtype == torch.uint8 and not (0 <= self.ignore_index <= 255):
                 inv_tw = 1.0 / float(B * H * W)  # nothing can be ignored: Σ v·w is the pixel count
+            elif self._prefetched is not None and self._prefetched[0] is target and self._prefetched[1] == C:
+                _, _, tw, ev = self._prefetched                   # pre-pass already running / done on the side stream
+                torch.cuda.current_stream(dev).wait_event(ev)
+                inv_tw_dev = tw[1:]
+                self._prefetched = None
             else:
                 tw = torch.empty(2, dtype=torch.float64, device=dev)
                 ops.label_hist(t, C, self.ignore_index, hist=None, weight=w, total_weight_out=tw)

@@ -296,3 +296,38 @@ def test_host_buffer_entry_point(dtype, pinned):
     loss2, _ = ctx.ce_fused(x, t, w, 255, want_grad=True, confmat=cm)
     assert loss2.item() == loss.item() and torch.equal(cm, 2 * ref.compute())
     ctx.close()
+
+
+def test_prefetched_total_weight_gives_identical_results():
+    """crit.prefetch_total_weight(target) moves the K4 pre-pass to a side stream ahead of time; loss and
+    gradients are bit-identical to the in-line pre-pass."""
+    from cvcs_b200.loss import FusedCrossEntropyLoss
+    torch.manual_seed(3)
+    C = 7
+    w = torch.rand(C) + 0.5
+    crit = FusedCrossEntropyLoss(weight=w, ignore_index=255).to(DEV)
+    x = torch.randn(2, C, 64, 64, device=DEV)
+    t = torch.randint(0, C, (2, 64, 64), device=DEV, dtype=torch.uint8)
+    t[0, :5] = 255
+    xa = x.clone().requires_grad_(True)
+    la = crit(xa, t)
+    la.backward()
+    xb = x.clone().requires_grad_(True)
+    crit.prefetch_total_weight(t, C)
+    lb = crit(xb, t)
+    lb.backward()
+    assert crit._prefetched is None
+    assert la.item() == lb.item() and torch.equal(xa.grad, xb.grad)
+    # a different target tensor does not pick up a stale prefetch
+    crit.prefetch_total_weight(t, C)
+    t2 = t.clone()
+    t2[1, :7] = 255
+    xc = x.clone().requires_grad_(True)
+    lc = crit(xc, t2)
+    lc.backward()
+    ref = torch_path.make_criterion(w, 255)
+    xr = x.detach().cpu().requires_grad_(True)
+    lr = ref(xr, t2.cpu().long())
+    lr.backward()
+    assert abs(lc.item() - lr.item()) <= 1e-5 * abs(lr.item())
+    assert float((xc.grad.cpu() - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
