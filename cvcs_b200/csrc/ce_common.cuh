@@ -275,9 +275,24 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
 
 #endif  // __CUDACC__
 
-// persistent grid = resident CTAs per SM x SMs
+// persistent grid = resident CTAs per SM x SMs.  The attribute call and the occupancy query cost a few
+// microseconds of host time each, so the answer is remembered per (kernel, threads, smem, device).
 template <typename K>
 int persistent_grid(K kernel, int threads, int smem_bytes, int* grid_out) {
+    struct Entry {
+        const void* fn;
+        int threads, smem, dev, grid;
+    };
+    static thread_local Entry cache[16];
+    static thread_local int n_cached = 0, next_slot = 0;
+    int dev = 0;
+    CVCS_CUDA_OK(cudaGetDevice(&dev));
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    for (int i = 0; i < n_cached; ++i)
+        if (cache[i].fn == fn && cache[i].threads == threads && cache[i].smem == smem_bytes && cache[i].dev == dev) {
+            *grid_out = cache[i].grid;
+            return CVCS_OK;
+        }
     int per_sm = 0;
     if (smem_bytes > 48 * 1024)
         CVCS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -286,6 +301,9 @@ int persistent_grid(K kernel, int threads, int smem_bytes, int* grid_out) {
     int g = per_sm * num_sms();
     if (g > kMaxGrid) g = kMaxGrid;
     *grid_out = g;
+    cache[next_slot] = Entry{fn, threads, smem_bytes, dev, g};
+    next_slot = (next_slot + 1) % 16;
+    if (n_cached < 16) ++n_cached;
     return CVCS_OK;
 }
 
