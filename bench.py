@@ -299,6 +299,8 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "tma", "direct", "generic"])
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--no-wait-hint", action="store_true", help="A/B: mbarrier waits without the suspend-time hint")
+    ap.add_argument("--reserve-sms", type=int, default=-1,
+                    help="SMs K1 leaves free for concurrent collectives (-1: 2 when a per-step all-reduce must overlap K1, else 0)")
     ap.add_argument("--ctas", type=int, default=0, help="A/B: CTAs per SM the TMA variant sizes its stages for")
     ap.add_argument("--vecp", type=int, default=0, help="A/B: pixels per consumer thread of the TMA variant (f32: 2|4, bf16: 4|8)")
     ap.add_argument("--label-dtype", default="u8", choices=["u8", "i64"])
@@ -361,19 +363,24 @@ def main():
     ii = wl["ignore_index"]
     data_dependent_tw = wl["weighted"] or (0 <= ii <= 255) or args.label_dtype == "i64"
     prepass_on = grad and data_dependent_tw
+    # a per-step collective (global Σw) has to run WHILE K1 runs: leave it two SMs (K1 claims chunks dynamically)
+    reserve = args.reserve_sms if args.reserve_sms >= 0 else (2 if (world > 1 and prepass_on) else 0)
+    _lib.set_option(_lib.OPT_RESERVE_SMS, reserve)
     # K4 pre-pass (Σ v·w[y] must be known before the first dlogit is written) runs ONE STEP AHEAD on its own
     # stream: the labels of the next batch are known while the current K1 runs (as in a training loop with a
     # prefetching loader), so the pre-pass — and at N > 1 its label-histogram all-reduce — overlaps K1.
     pre = torch.cuda.Stream(device=dev) if prepass_on else None
     tws = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(n_sets)]
-    hists = [torch.zeros(C + 2, dtype=torch.int64, device=dev) for _ in range(n_sets)]
+    tw_sum = [t_[0:1] for t_ in tws]     # views made once: the per-step Python path is the bottleneck at N > 1
+    tw_inv = [t_[1:2] for t_ in tws]
     pre_ready = [None] * n_sets      # event on `pre`: tws[j] holds this step's total weight
     k1_done = [None] * n_sets        # event on the main stream: the K1 that read tws[j] has run
     issued = {"upto": -1}
-    side = torch.cuda.Stream(device=dev) if world > 1 else None
-    sums_sets = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(n_sets)]
-    sums = sums_sets[0]
-    sums_comm = torch.zeros(3, dtype=torch.float64, device=dev)
+    # per-step loss sums f64[3] land in a [rows, 3] table; at N > 1 the table is all-reduced ONCE per pass
+    # (the global per-step losses are what a training loop logs — nothing on the data path waits for them, and a
+    # collective per step would have to squeeze its kernel in between back-to-back persistent K1 launches)
+    sums_rows = max(args.steps, args.warmup, 1)
+    sums_table = torch.zeros((sums_rows, 3), dtype=torch.float64, device=dev)
     launches = {"n": 0}
     k1_events = []
 
@@ -384,11 +391,10 @@ def main():
             pre.wait_event(k1_done[j])
         with torch.cuda.stream(pre):
             if world > 1:
-                hists[j].zero_()
-                ops.label_hist(t, C, ii, hist=hists[j])
-                dist.all_reduce(hists[j])                       # global Σw: results equal the 1-process run
-                ops.total_weight(hists[j], weight, C, ii, out=tws[j])
-                launches["n"] += 2
+                ops.label_hist(t, C, ii, weight=weight, total_weight_out=tws[j])    # this rank's Σ v·w[y] (fp64)
+                dist.all_reduce(tw_sum[j])                      # global Σw: every rank divides by the same total
+                torch.reciprocal(tw_sum[j], out=tw_inv[j])
+                launches["n"] += 1
             else:
                 ops.label_hist(t, C, ii, weight=weight, total_weight_out=tws[j])
                 launches["n"] += 1
@@ -406,14 +412,14 @@ def main():
                 if issued["upto"] < i:
                     prepass(i)
                 torch.cuda.current_stream(dev).wait_event(pre_ready[j])
-                inv_dev = tws[j][1:]
+                inv_dev = tw_inv[j]
             else:
                 inv = 1.0 / float(px_per_gpu * world)           # nothing can be ignored: Σw = global pixel count
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         ops.ce_fused(x, t, weight, ii, want_grad=grad, inv_total_weight=inv, inv_total_weight_dev=inv_dev,
-                     dlogits=dl[j], argmax=am[j], confmat=confmat, loss_sums=sums_sets[j], loss_out=loss_out)
+                     dlogits=dl[j], argmax=am[j], confmat=confmat, loss_sums=sums_table[i % sums_rows], loss_out=loss_out)
         launches["n"] += 1
         if timed:
             e1.record()
@@ -423,20 +429,10 @@ def main():
             k1_done[j].record()
             if not last:
                 prepass(i + 1)
-        if world > 1:
-            # global loss of this step: f64[3] all-reduce on a side stream, overlapped with the next K1
-            ev = torch.cuda.Event()
-            ev.record()
-            side.wait_event(ev)
-            with torch.cuda.stream(side):
-                sums_comm.copy_(sums_sets[j])
-                dist.all_reduce(sums_comm)
-
     def fence():
         if pre is not None:
             torch.cuda.current_stream(dev).wait_stream(pre)
         if world > 1:
-            torch.cuda.current_stream(dev).wait_stream(side)
             dist.barrier()
         torch.cuda.synchronize(dev)
 
@@ -450,12 +446,14 @@ def main():
     sampler.start()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         step(i, True, last=(i == args.steps - 1))
+    host_ms_per_step = (time.perf_counter() - host_t0) * 1e3 / args.steps   # enqueue cost; must stay below ms_per_step
     if pre is not None:
         torch.cuda.current_stream(dev).wait_stream(pre)
     if world > 1:
-        torch.cuda.current_stream(dev).wait_stream(side)
+        dist.all_reduce(sums_table)                             # every step's global loss sums, one collective
         dist.all_reduce(confmat)                                # one C*C all-reduce per pass
     end.record()
     fence()
@@ -543,10 +541,11 @@ def main():
             "config": {"workload": f"{args.workload}: {wl['desc']}", "per_gpu_batch": B, "classes": C,
                        "tile": [H, W], "labels": args.label_dtype + " (blocky 32x32)", "grad": grad, "layout": args.layout,
                        "l2": f"inputs larger than L2: {n_sets} rotating sets of {px_per_gpu * C * esize * (2 if grad else 1) / 1e6:.0f} MB",
-                       "parallelism": f"dp{world}: tiles sharded per GPU; f64[3] loss all-reduce per step (side stream) + "
+                       "parallelism": f"dp{world}: tiles sharded per GPU; one all-reduce of the [steps,3] f64 loss-sum table + "
                                       "one CxC confusion all-reduce per pass" if world > 1 else "single GPU",
-                       "k4_prepass": "one step ahead on a side stream (overlaps K1)" if prepass_on else False, "path": args.path},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+                       "k4_prepass": "one step ahead on a side stream (overlaps K1)" if prepass_on else False, "path": args.path,
+                       "sms_reserved_for_collectives": reserve},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "host_enqueue_ms_per_step": host_ms_per_step,
             "clocks": sampler.summary(),
             "check": {"confusion_total": total_cm, "loss": float(loss_out.item())},
         }

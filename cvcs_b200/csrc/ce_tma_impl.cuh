@@ -541,6 +541,12 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
         p.items_per_image = static_cast<unsigned int>((p.hw + P - 1) / P);
         p.n_items = static_cast<long long>(p.items_per_image) * (p.n_pixels / p.hw);
     }
+    {   // leave whole SMs free when asked to (a concurrent collective needs somewhere to run); chunks are
+        // claimed dynamically, so any grid size does the same work
+        const int reserve = get_option(CVCS_OPT_RESERVE_SMS);
+        const int sms = num_sms();
+        if (reserve > 0 && reserve <= 32 && reserve < sms) grid -= (grid / sms) * reserve;
+    }
     if (p.n_items < grid) grid = static_cast<int>(p.n_items < 1 ? 1 : p.n_items);
     kernel<<<grid, kBlock, smem, stream>>>(p, g);
     CVCS_CUDA_OK(cudaGetLastError());

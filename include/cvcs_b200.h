@@ -93,7 +93,8 @@ enum cvcs_option {
     CVCS_OPT_TMA_VECP = 3,   /* NCHW, C <= 8: pixels per consumer thread (0 = default; f32: 2|4, bf16: 4|8) */
     CVCS_OPT_TMA_CTAS = 4,   /* CTAs per SM the TMA variant sizes its stages for (0 = default 2; 1..4)      */
     CVCS_OPT_TILE_CTAS = 5,  /* K5: CTAs per SM of the persistent grid (0 = default; 1..8)                  */
-    CVCS_OPT_COUNT = 6
+    CVCS_OPT_RESERVE_SMS = 6, /* K1: SMs left free (e.g. for an NCCL kernel that must run concurrently); 0..32   */
+    CVCS_OPT_COUNT = 7
 };
 int cvcs_set_option(int option, int value);
 
