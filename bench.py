@@ -438,6 +438,9 @@ def main():
 
     for i in range(args.warmup):
         step(i, False, last=(i == args.warmup - 1))
+    if world > 1:                                               # warm the pass-end collectives up too
+        dist.all_reduce(sums_table)
+        dist.all_reduce(confmat)
     fence()
     confmat.zero_()
     launches["n"] = 0
