@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--label-dtype", default="u8", choices=["u8", "i64"])
     ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"], help="logits memory format (nhwc = torch channels_last)")
     ap.add_argument("--no-grad", action="store_true", help="forward/eval only (no dlogits)")
+    ap.add_argument("--metrics-only", action="store_true", help="K1 metrics mode: argmax + confusion matrix, no loss (cvcs_eval_fused)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-copy-ref", action="store_true", help="skip the same-size torch copy reference measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -348,7 +349,7 @@ def main():
     B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
     esize = 4 if wl["dtype"] == "f32" else 2
     px_per_gpu = B * H * W
-    grad = not args.no_grad
+    grad = not (args.no_grad or args.metrics_only)
     n_sets = 3   # rotate buffer sets; each set (logits + dlogits) is far larger than the 126 MB L2 anyway
     sets, weight = synth_inputs(torch, wl, dev, seed=1234 + rank, n_sets=n_sets)
     if args.label_dtype == "i64":
@@ -418,8 +419,11 @@ def main():
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        ops.ce_fused(x, t, weight, ii, want_grad=grad, inv_total_weight=inv, inv_total_weight_dev=inv_dev,
-                     dlogits=dl[j], argmax=am[j], confmat=confmat, loss_sums=sums_table[i % sums_rows], loss_out=loss_out)
+        if args.metrics_only:
+            ops.eval_fused(x, t, ii, argmax=am[j], confmat=confmat)
+        else:
+            ops.ce_fused(x, t, weight, ii, want_grad=grad, inv_total_weight=inv, inv_total_weight_dev=inv_dev,
+                         dlogits=dl[j], argmax=am[j], confmat=confmat, loss_sums=sums_table[i % sums_rows], loss_out=loss_out)
         launches["n"] += 1
         if timed:
             e1.record()
@@ -542,7 +546,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": wl["dtype"], "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "per_gpu_batch": B, "classes": C,
-                       "tile": [H, W], "labels": args.label_dtype + " (blocky 32x32)", "grad": grad, "layout": args.layout,
+                       "tile": [H, W], "labels": args.label_dtype + " (blocky 32x32)", "grad": grad, "metrics_only": args.metrics_only, "layout": args.layout,
                        "l2": f"inputs larger than L2: {n_sets} rotating sets of {px_per_gpu * C * esize * (2 if grad else 1) / 1e6:.0f} MB",
                        "parallelism": f"dp{world}: tiles sharded per GPU; one all-reduce of the [steps,3] f64 loss-sum table + "
                                       "one CxC confusion all-reduce per pass" if world > 1 else "single GPU",

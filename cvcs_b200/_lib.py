@@ -52,6 +52,7 @@ SIGNATURES = {
     "cvcs_total_weight": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
     "cvcs_ce_fused": (_i, [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _vp,
                            _vp, _vp, _vp]),
+    "cvcs_eval_fused": (_i, [_vp, _i, _i, _vp, _i, _ll, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "cvcs_scale_inplace": (_i, [_vp, _i, _ll, _vp, _vp]),
     "cvcs_argmax": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "cvcs_confmat": (_i, [_vp, _i, _vp, _i, _ll, _i, _ll, _vp, _vp, _vp, _vp]),

@@ -37,7 +37,8 @@ int num_sms() {
 
 // launchers implemented in the kernel translation units
 int ce_fused_launch(const void*, int, int, const void*, int, const float*, long long, int, int, int, int, double,
-                    const double*, void*, void*, int, unsigned long long*, double*, float*, void*, cudaStream_t);
+                    const double*, void*, void*, int, unsigned long long*, double*, float*, void*, cudaStream_t,
+                    unsigned long long* status = nullptr, int no_loss = 0);
 int label_hist_launch(const void*, int, long long, int, long long, unsigned long long*, const float*, double*, void*,
                       cudaStream_t);
 int total_weight_launch(const unsigned long long*, const float*, int, long long, double*, cudaStream_t);
@@ -132,6 +133,15 @@ int cvcs_ce_fused(const void* logits_dev, int logits_dtype, int layout, const vo
     return ce_fused_launch(logits_dev, logits_dtype, layout, target_dev, target_dtype, weight_dev, ignore_index, B, C, H,
                            W, inv_total_weight, inv_total_weight_dev, dlogits_dev, argmax_dev, argmax_dtype, confmat_dev,
                            loss_sums_dev, loss_out_dev, workspace_dev, static_cast<cudaStream_t>(stream));
+}
+
+int cvcs_eval_fused(const void* logits_dev, int logits_dtype, int layout, const void* target_dev, int target_dtype,
+                    long long ignore_index, int B, int C, int H, int W, void* argmax_dev, int argmax_dtype,
+                    unsigned long long* confmat_dev, unsigned long long* status_dev, void* workspace_dev, void* stream) {
+    CVCS_REQUIRE(argmax_dev || confmat_dev, "cvcs_eval_fused: nothing to compute (argmax and confmat both NULL)");
+    return ce_fused_launch(logits_dev, logits_dtype, layout, target_dev, target_dtype, nullptr, ignore_index, B, C, H, W,
+                           0.0, nullptr, nullptr, argmax_dev, argmax_dtype, confmat_dev, nullptr, nullptr, workspace_dev,
+                           static_cast<cudaStream_t>(stream), status_dev, 1);
 }
 
 int cvcs_scale_inplace(void* x_dev, int dtype, long long n, const float* scale_dev, void* stream) {

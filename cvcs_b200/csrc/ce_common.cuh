@@ -30,6 +30,8 @@ struct CeParams {
     int target_i64;  // 0: u8, 1: i64
     int argmax_i64;  // 0: u8, 1: i64
     int conf_reps;   // generic kernel: shared-memory replicas of the C*C bins (0 = global atomics)
+    unsigned long long* status;  // nullable: += #out-of-bounds labels (metrics mode, cvcs_eval_fused)
+    int no_loss;     // 1: metrics mode — argmax + confusion matrix only, no softmax / loss (loss_sums may be NULL)
 };
 
 // launchers (one translation unit each)
@@ -258,9 +260,12 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
             b += red[NWARPS + w];
         }
         const unsigned long long nbad = atomicAdd(&p.ws->bad, 0ull);
-        p.loss_sums[0] = a;
-        p.loss_sums[1] = b;
-        p.loss_sums[2] = static_cast<double>(nbad);
+        if (p.status && nbad) atomicAdd(p.status, nbad);
+        if (p.loss_sums) {
+            p.loss_sums[0] = a;
+            p.loss_sums[1] = b;
+            p.loss_sums[2] = static_cast<double>(nbad);
+        }
         if (p.loss_out) {
             float l = static_cast<float>(a / b);  // 0/0 -> NaN like torch (everything ignored)
             if (nbad) l = __int_as_float(0x7fc00000);
@@ -294,8 +299,16 @@ int persistent_grid(K kernel, int threads, int smem_bytes, int* grid_out) {
             return CVCS_OK;
         }
     int per_sm = 0;
-    if (smem_bytes > 48 * 1024)
-        CVCS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    // opt in to the architectural maximum once (227 KB on sm_100a) rather than to this call's size: the
+    // attribute is per kernel, and a later, smaller request must not lower it under a cached larger one
+    if (smem_bytes > 48 * 1024) {
+        cudaFuncAttributes fa;
+        CVCS_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
+        const int max_dyn = 227 * 1024 - static_cast<int>(fa.sharedSizeBytes);   // static + dynamic <= 227 KB
+        if (smem_bytes > max_dyn)
+            return set_error(CVCS_ERR_UNSUPPORTED, "kernel needs %d B of dynamic shared memory, %d available", smem_bytes, max_dyn);
+        CVCS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    }
     CVCS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes));
     if (per_sm < 1) return set_error(CVCS_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %d B)", smem_bytes);
     int g = per_sm * num_sms();

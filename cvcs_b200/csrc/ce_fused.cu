@@ -18,8 +18,9 @@ int ce_fused_launch(const void* logits, int logits_dtype, int layout, const void
                     const float* weight, long long ignore_index, int B, int C, int H, int W,
                     double inv_total_weight, const double* inv_total_weight_dev, void* dlogits, void* argmax,
                     int argmax_dtype, unsigned long long* confmat, double* loss_sums, float* loss_out,
-                    void* workspace, cudaStream_t stream) {
-    CVCS_REQUIRE(logits && target && loss_sums && workspace, "cvcs_ce_fused: NULL logits/target/loss_sums/workspace");
+                    void* workspace, cudaStream_t stream, unsigned long long* status, int no_loss) {
+    CVCS_REQUIRE(logits && target && (loss_sums || no_loss) && workspace, "cvcs_ce_fused: NULL logits/target/loss_sums/workspace");
+    CVCS_REQUIRE(!(no_loss && dlogits), "cvcs_eval_fused: metrics mode has no gradients");
     CVCS_REQUIRE(logits_dtype == CVCS_F32 || logits_dtype == CVCS_BF16, "cvcs_ce_fused: logits dtype tag %d (want f32/bf16)", logits_dtype);
     CVCS_REQUIRE(layout == CVCS_NCHW || layout == CVCS_NHWC, "cvcs_ce_fused: layout %d", layout);
     CVCS_REQUIRE(target_dtype == CVCS_U8 || target_dtype == CVCS_I64,
@@ -51,6 +52,8 @@ int ce_fused_launch(const void* logits, int logits_dtype, int layout, const void
     p.C = C;
     p.target_i64 = target_dtype == CVCS_I64;
     p.argmax_i64 = argmax_dtype == CVCS_I64;
+    p.status = status;
+    p.no_loss = no_loss;
 
     const int forced = get_option(CVCS_OPT_CE_PATH);  // 0 auto, 1 tma, 2 direct, 3 generic
     const int esize = logits_dtype == CVCS_F32 ? 4 : 2;

@@ -169,7 +169,7 @@ __device__ __forceinline__ void sts_elem(unsigned char* base, int idx, float v) 
     else *reinterpret_cast<unsigned short*>(base + 2 * idx) = static_cast<unsigned short>(pack_bf16(v, 0.f) & 0xffffu);
 }
 
-template <typename T, int C, int VECP, bool NHWC, bool PRIV, bool GRAD>
+template <typename T, int C, int VECP, bool NHWC, bool PRIV, bool GRAD, bool LOSS = true>
 __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, const Geom g) {
     constexpr int P = kThreads * VECP;
     constexpr int ES = sizeof(T);
@@ -390,18 +390,38 @@ __global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, con
                         bad += (!valid && tv != -1) ? 1u : 0u;
                         const int tc = valid ? tv : 0;
                         // the target logit and its class weight by dynamic index from shared memory
-                        const float xt = lds_elem<T>(stage, eidx(tc, pix_t0 + k));
-                        const float w = valid ? wsm[tc] : 0.f;
+                        float xt = 0.f, w = 0.f;
+                        if constexpr (LOSS) {
+                            xt = lds_elem<T>(stage, eidx(tc, pix_t0 + k));
+                            w = valid ? wsm[tc] : 0.f;
+                        }
 #pragma unroll
                         for (int c = 0; c < C; ++c) x[q][c] = raw_get(ridx(c, k));
                         float m, s;
                         int arg;
-                        softmax_core<C, ES == 2>(x[q], m, s, arg);
+                        if constexpr (LOSS) {
+                            softmax_core<C, ES == 2>(x[q], m, s, arg);
+                        } else {
+                            // metrics mode: only the argmax is wanted.  Σ x is NaN exactly when the row holds a NaN
+                            // (or +inf and -inf together): those rows take the NaN-aware path below
+                            m = x[q][0];
+                            s = x[q][0];
+#pragma unroll
+                            for (int c = 1; c < C; ++c) {
+                                m = fmaxf(m, x[q][c]);
+                                s += x[q][c];
+                            }
+                            arg = C - 1;
+#pragma unroll
+                            for (int c = C - 2; c >= 0; --c) arg = (x[q][c] == m) ? c : arg;
+                        }
                         anomalous |= (s != s);
                         amax[k] = arg;
-                        const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
-                        step_l += valid ? w * nll : 0.f;
-                        step_w += w;
+                        if constexpr (LOSS) {
+                            const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
+                            step_l += valid ? w * nll : 0.f;
+                            step_w += w;
+                        }
                         r[q] = 0.f;
                         if constexpr (do_grad) {
                             const float gsc = valid ? w * inv_tw : 0.f;  // exact zeros at ignored pixels
@@ -531,7 +551,8 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     // (more bytes in flight per SM than ~120 KB measurably lowers the sustained HBM rate)
     const int min_smem = 233472 / (target_ctas + 1) - 1024 + 16;
     if (smem < min_smem) smem = min_smem;
-    auto kernel = p.dlogits ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, true> : ce_tma_kernel<T, C, VECP, NHWC, PRIV, false>;
+    auto kernel = p.dlogits ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, true>
+                            : (p.no_loss ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, false, false> : ce_tma_kernel<T, C, VECP, NHWC, PRIV, false, true>);
     int grid = 0;
     int rc = persistent_grid(kernel, kBlock, smem, &grid);
     if (rc) return rc;

@@ -103,7 +103,8 @@ class MulticlassConfusionMatrix:
         ops.confmat_update(cm, preds, target, self.num_classes, self.ignore_index, status=self._s["status"])
 
     def update_from_logits(self, logits: torch.Tensor, target: torch.Tensor) -> None:
-        """Fused argmax + confusion update straight from [B,C,H,W] (or [C,H,W]) logits (K1, forward only)."""
+        """Fused argmax + confusion update straight from [B,C,H,W] (or [C,H,W]) logits (K1, metrics mode:
+        one read of the logits, no softmax)."""
         dev = self._target_device(logits, target)
         logits, target = logits.to(dev), target.to(dev)
         if logits.dim() == 3:
@@ -118,9 +119,7 @@ class MulticlassConfusionMatrix:
         if target.dtype not in (torch.uint8, torch.int64):
             target = target.to(torch.int64)
         cm = self._state_for(dev, C)
-        ign = -(1 << 62) if self.ignore_index is None else int(self.ignore_index)
-        _, sums, _ = ops.ce_fused(logits, target, None, ign, want_grad=False, confmat=cm)
-        self._s["status"] += sums[2:3].to(torch.int64)
+        ops.eval_fused(logits, target, self.ignore_index, confmat=cm, status=self._s["status"])
 
     __call__ = update
 

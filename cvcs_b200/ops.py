@@ -133,6 +133,26 @@ def ce_fused(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.
     return loss_out, loss_sums, (dlogits if want_grad else None)
 
 
+def eval_fused(logits: torch.Tensor, target: torch.Tensor, ignore_index: Optional[int] = None, *,
+               argmax: Optional[torch.Tensor] = None, confmat: Optional[torch.Tensor] = None,
+               status: Optional[torch.Tensor] = None) -> None:
+    """K1 in metrics mode: argmax map and / or confusion-matrix update from [B,C,H,W] logits in one read
+    (no softmax, no loss) — what ``utils.eval_model`` does per tile (utils.py:88-94)."""
+    dev = _need_cuda(logits, target, argmax, confmat, status)
+    if logits.dim() != 4:
+        raise RuntimeError(f"cvcs_b200.eval_fused expects [B,C,H,W] logits, got {tuple(logits.shape)}")
+    B, Cc, H, W = logits.shape
+    if tuple(target.shape) != (B, H, W):
+        raise RuntimeError(f"size mismatch (got input: {list(logits.shape)} , target: {list(target.shape)}")
+    logits, layout = logits_layout(logits)
+    target = target.contiguous()
+    ign = -(1 << 62) if ignore_index is None else int(ignore_index)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_eval_fused(logits.data_ptr(), _tag(logits), layout, target.data_ptr(), _tag(target), ign, B, Cc, H,
+                                  W, _ptr(argmax), _tag(argmax) if argmax is not None else _lib.U8, _ptr(confmat),
+                                  _ptr(status), workspace(dev).data_ptr(), _stream(dev)))
+
+
 def scale_inplace(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     dev = _need_cuda(x, scale)
     assert scale.dtype == torch.float32 and scale.numel() == 1

@@ -11,6 +11,7 @@
  *                            loss.backward()                    train.py:125
  *                            torch.max(y_pred, dim=0)           utils.py:90
  *                            MulticlassConfusionMatrix.update   utils.py:93-94
+ *   cvcs_eval_fused       <- torch.max + MulticlassConfusionMatrix.update x2   utils.py:88-94 (eval_model)
  *   cvcs_scale_inplace    <- autograd's grad_output * dlogits (only when grad_output != 1)
  *   cvcs_argmax           <- torch.argmax(..., dim=2)           utils.py:158,504  esa.py:56
  *   cvcs_confmat          <- MulticlassConfusionMatrix.update   utils.py:93-94 (index inputs)
@@ -138,6 +139,16 @@ int cvcs_ce_fused(const void* logits_dev, int logits_dtype, int layout, const vo
                   void* dlogits_dev, void* argmax_dev, int argmax_dtype,
                   unsigned long long* confmat_dev, double* loss_sums_dev, float* loss_out_dev,
                   void* workspace_dev, void* stream);
+
+/* ---- K1, metrics mode: argmax + confusion matrix straight from logits, no softmax / loss -----------
+ * What utils.eval_model needs per tile (utils.py:88-94: torch.max + two MulticlassConfusionMatrix
+ * updates): one read of the logits, the u8 / i64 argmax map (nullable) and the C x C update
+ * (nullable, accumulated).  status_dev: nullable u64[1], += #labels outside [0, C) that are not
+ * ignore_index (torchmetrics' validate_args, checked lazily by the caller). */
+int cvcs_eval_fused(const void* logits_dev, int logits_dtype, int layout, const void* target_dev,
+                    int target_dtype, long long ignore_index, int B, int C, int H, int W,
+                    void* argmax_dev, int argmax_dtype, unsigned long long* confmat_dev,
+                    unsigned long long* status_dev, void* workspace_dev, void* stream);
 
 /* x[i] *= *scale_dev, in place (x: CVCS_F32 or CVCS_BF16). */
 int cvcs_scale_inplace(void* x_dev, int dtype, long long n, const float* scale_dev, void* stream);

@@ -239,3 +239,45 @@ def test_stitch_vector_path_with_center_crop():
     yx = torch.tensor([[0, 0], [0, 24], [24, 48], [56, 80], [-8, 100], [72, -4]], dtype=torch.int32)
     out = ops.stitch(tiles.to(DEV), yx.to(DEV), (H, W), crop_hw=(ch, ch))
     assert np.array_equal(out.cpu().numpy(), c_oracle.stitch(tiles.numpy(), yx.numpy(), H, W, crop=(ch, ch)))
+
+
+@pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
+@pytest.mark.parametrize("dtype,label_dtype", [(torch.float32, torch.uint8), (torch.float32, torch.int64), (torch.bfloat16, torch.uint8)])
+@pytest.mark.parametrize("C,H,W", [(7, 64, 128), (16, 48, 80), (20, 32, 64), (5, 37, 41)])
+def test_eval_fused_metrics_mode(layout, dtype, label_dtype, C, H, W):
+    """cvcs_eval_fused (K1 without softmax / loss): argmax map + confusion matrix in one read of the logits,
+    bit-exact vs the oracle, including rows with NaN / inf, ties, ignored and out-of-range labels."""
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(C * H + W)
+    B = 3
+    x = (torch.randn(B, C, H, W, generator=g) * 3).to(dtype).float()
+    x[0, :, 0, :8] = 1.0                                         # ties -> first index
+    x[0, 2, 1, :4] = float("nan")                                # NaN is maximal, first NaN wins
+    x[0, 4, 1, 2:6] = float("nan")
+    x[1, 1, 2, :3] = float("inf")
+    x[1, 3, 2, 1:5] = float("-inf")
+    x[2, :, 3, :2] = float("-inf")
+    t = torch.randint(0, C, (B, H, W), generator=g)
+    t[0, 5] = 255                                                # ignored
+    t[1, 6, :3] = C + 1                                          # out of range -> status
+    xd = x.to(dtype).to(DEV)
+    if layout == "NHWC":
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    td = t.to(label_dtype).to(DEV)
+    am = torch.full((B, H, W), 99, dtype=torch.uint8, device=DEV)
+    cm = torch.zeros((C, C), dtype=torch.int64, device=DEV)
+    st = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ops.eval_fused(xd, td, 255, argmax=am, confmat=cm, status=st)
+    am_ref = c_oracle.argmax(x.numpy())
+    assert np.array_equal(am.cpu().numpy().astype(np.int64), am_ref)
+    keep = (t.numpy() != C + 1)
+    cm_ref, _ = c_oracle.confmat(am_ref[keep], t.numpy()[keep], C, 255)
+    assert np.array_equal(cm.cpu().numpy(), cm_ref)
+    assert int(st.item()) == 3
+    # confusion only / argmax only
+    cm2 = torch.zeros_like(cm)
+    ops.eval_fused(xd, td, 255, confmat=cm2)
+    assert torch.equal(cm2, cm)
+    am64 = torch.empty((B, H, W), dtype=torch.int64, device=DEV)
+    ops.eval_fused(xd, td, None, argmax=am64)
+    assert np.array_equal(am64.cpu().numpy(), am_ref)
