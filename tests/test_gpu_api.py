@@ -2,6 +2,7 @@
 nn.CrossEntropyLoss (utils.py:223-242, train.py:122-125), MulticlassConfusionMatrix + eval_model
 (utils.py:59-103), validation_loss (utils.py:106-126), the host-buffer C-ABI entry point."""
 import io
+import os
 import pickle
 
 import numpy as np
@@ -331,3 +332,19 @@ def test_prefetched_total_weight_gives_identical_results():
     lr.backward()
     assert abs(lc.item() - lr.item()) <= 1e-5 * abs(lr.item())
     assert float((xc.grad.cpu() - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
+
+
+def test_c_abi_from_a_plain_c_host(tmp_path):
+    """A non-Python caller: a C program (gcc, no CUDA or torch headers) dlopens the library and drives
+    cvcs_host_ce_fused on malloc'ed host buffers, checking against its own scalar restatement."""
+    import shutil
+    import subprocess
+    from cvcs_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "c_abi_host_demo")
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c_abi_host_demo.c"),
+                    "-o", exe, "-ldl", "-lm"], check=True)
+    r = subprocess.run([exe, _lib.LIB_PATH], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "C-ABI DEMO OK" in r.stdout, r.stdout + r.stderr
