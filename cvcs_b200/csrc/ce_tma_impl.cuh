@@ -170,7 +170,7 @@ __device__ __forceinline__ void sts_elem(unsigned char* base, int idx, float v) 
 }
 
 template <typename T, int C, int VECP, bool NHWC, bool PRIV, bool GRAD, bool LOSS = true>
-__global__ void __launch_bounds__(kBlock, 2) ce_tma_kernel(const CeParams p, const Geom g) {
+__global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CeParams p, const Geom g) {
     constexpr int P = kThreads * VECP;
     constexpr int ES = sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
@@ -526,10 +526,14 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     // sustained HBM rate peaks when the stages resident on an SM total ~90-125 KB and falls off on either
     // side (59 KB: 0.74, 89 KB: 0.90, 119 KB: 0.84, 178 KB: 0.83 of the measured copy peak for fp32 C=7):
     // 3 stages per CTA, and 2 CTAs per SM only while 2 x 3 stages stay within 128 KB.  Forward-only
-    // (read stream only) wants as much in flight as fits: 2 CTAs, as many stages as the budget allows.
+    // (read stream only, issue-bound) wants warps and bytes in flight: 3 CTAs when 3 stages each still
+    // fit (C=20: 0.58 -> 0.72 of peak), else 2 CTAs with as many stages as the budget allows.
     const bool grad = p.dlogits != nullptr;
     int target_ctas = get_option(CVCS_OPT_TMA_CTAS);
-    if (target_ctas < 1 || target_ctas > 4) target_ctas = (grad && 2 * 3 * g.stage_bytes > 128 * 1024) ? 1 : 2;
+    if (target_ctas < 1 || target_ctas > 4) {
+        if (grad) target_ctas = (2 * 3 * g.stage_bytes > 128 * 1024) ? 1 : 2;
+        else target_ctas = ((233472 / 3 - 2048 - g.stage_off) / g.stage_bytes >= 3) ? 3 : 2;  // forward-only kernels fit 3 CTAs (64 regs)
+    }
     const int per_cta = 233472 / target_ctas - 1024 - 1024;  // 228 KB per SM, 1 KB reserved per CTA, static smem
     int stages = (per_cta - g.stage_off) / g.stage_bytes;
     if (stages < 3 && target_ctas > 1) {  // wide stages (i64 labels, large C): the whole SM
