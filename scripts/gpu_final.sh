@@ -9,7 +9,7 @@ timeout 2400 python -m pytest tests -m gpu -q --tb=short --timeout 600 -p no:cac
 tail -3 gpurun_out/pytest.log
 timeout 600 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench rc=$?" | tee -a gpurun_out/summary.txt
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.log 2>&1; echo "bench ref rc=$?" | tee -a gpurun_out/summary.txt
-for v in "" "--path direct" "--workload cfg3" "--workload cfg5" "--no-grad" "--label-dtype i64" "--layout nhwc" "--layout nhwc --workload cfg3" "--layout nhwc --workload cfg5" "--batch 64" "--workload tile13" "--workload tile3"; do
+for v in "" "--path direct" "--workload cfg3" "--workload cfg5" "--no-grad" "--metrics-only" "--metrics-only --workload cfg5" "--label-dtype i64" "--layout nhwc" "--layout nhwc --workload cfg3" "--layout nhwc --workload cfg5" "--batch 64" "--workload tile13" "--workload tile3"; do
   echo "== $v" >> gpurun_out/bench_variants.log
   timeout 300 python bench.py --steps 100 --warmup 10 --no-e2e --no-cpu-baseline $v >> gpurun_out/bench_variants.log 2>&1
 done
