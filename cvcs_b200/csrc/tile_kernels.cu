@@ -252,10 +252,9 @@ __global__ void __launch_bounds__(kThreads) tile_kernel_scalar(const TileParams 
 // ---- N2 stitch -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) stitch_kernel(const unsigned char* __restrict__ tiles, int n_tiles, int th,
                                                           int tw, const int* __restrict__ yx, int ch, int cw,
-                                                          unsigned char* __restrict__ scene, int H, int W) {
+                                                          unsigned char* __restrict__ scene, int H, int W, int oy, int ox) {
     const long long per_tile = static_cast<long long>(ch) * cw;
     const long long total = per_tile * n_tiles;
-    const int oy = (th - ch) / 2, ox = (tw - cw) / 2;  // CenterCrop offsets (utils.py:146,154)
     for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * kThreads) {
         const int t = static_cast<int>(i / per_tile);
@@ -271,11 +270,10 @@ __global__ void __launch_bounds__(kThreads) stitch_kernel(const unsigned char* _
 // bases; a group whose destination is not 4-aligned or leaves the scene falls back to byte stores.
 __global__ void __launch_bounds__(kThreads) stitch_x4_kernel(const unsigned char* __restrict__ tiles, int n_tiles, int th,
                                                              int tw, const int* __restrict__ yx, int ch, int cw,
-                                                             unsigned char* __restrict__ scene, int H, int W) {
+                                                             unsigned char* __restrict__ scene, int H, int W, int oy, int ox) {
     const int gpr = cw / 4;  // groups per cropped row
     const long long per_tile = static_cast<long long>(ch) * gpr;
     const long long total = per_tile * n_tiles;
-    const int oy = (th - ch) / 2, ox = (tw - cw) / 2;
     for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * kThreads) {
         const int t = static_cast<int>(i / per_tile);
@@ -490,11 +488,13 @@ int stitch_launch(const unsigned char* tiles, int n_tiles, int th, int tw, const
     CVCS_REQUIRE(n_tiles >= 0 && th > 0 && tw > 0 && ch > 0 && cw > 0 && ch <= th && cw <= tw && H > 0 && W > 0, "cvcs_stitch: bad shape");
     if (n_tiles == 0) return CVCS_OK;
     const long long total = static_cast<long long>(n_tiles) * ch * cw;
-    const int ox = (tw - cw) / 2;
+    // torchvision's CenterCrop offset (utils.py:146,154): int(round(d / 2.0)) with Python's round-half-to-even
+    auto center = [](int d) { const int k = d / 2; return (d % 2 == 0 || k % 2 == 0) ? k : k + 1; };
+    const int oy = center(th - ch), ox = center(tw - cw);
     const bool x4 = cw % 4 == 0 && tw % 4 == 0 && ox % 4 == 0 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(tiles) & 3u) == 0 &&
                     (reinterpret_cast<uintptr_t>(scene) & 3u) == 0;
-    if (x4) stitch_x4_kernel<<<simple_grid(total / 4), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W);
-    else stitch_kernel<<<simple_grid(total), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W);
+    if (x4) stitch_x4_kernel<<<simple_grid(total / 4), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W, oy, ox);
+    else stitch_kernel<<<simple_grid(total), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W, oy, ox);
     CVCS_CUDA_OK(cudaGetLastError());
     return CVCS_OK;
 }

@@ -209,7 +209,10 @@ void oracle_colorize(const int64_t* idx, int64_t n, const float* lut, int64_t C,
 /* paste the centred ch x cw window of every th x tw tile at (yx[2k], yx[2k+1]); clip to the scene */
 void oracle_stitch(const uint8_t* tiles, int64_t n, int64_t th, int64_t tw, const int32_t* yx, int64_t ch, int64_t cw,
                    uint8_t* scene, int64_t H, int64_t W) {
-    const int64_t oy = (th - ch) / 2, ox = (tw - cw) / 2;
+    /* torchvision CenterCrop: int(round(d / 2.0)), Python rounds halves to even */
+    const int64_t ky = (th - ch) / 2, kx = (tw - cw) / 2;
+    const int64_t oy = ((th - ch) % 2 == 0 || ky % 2 == 0) ? ky : ky + 1;
+    const int64_t ox = ((tw - cw) % 2 == 0 || kx % 2 == 0) ? kx : kx + 1;
     for (int64_t k = 0; k < n; ++k)
         for (int64_t y = 0; y < ch; ++y)
             for (int64_t x = 0; x < cw; ++x) {

@@ -190,3 +190,15 @@ def test_vote_colorize_stitch(golden):
     tiles = np.arange(2 * 6 * 6, dtype=np.uint8).reshape(2, 6, 6)
     scene = c_oracle.stitch(tiles, np.array([[0, 0], [0, 4]]), 4, 8, crop=(4, 4))
     assert np.array_equal(scene[:, :4], tiles[0, 1:5, 1:5]) and np.array_equal(scene[:, 4:], tiles[1, 1:5, 1:5])
+
+
+def test_stitch_center_offset_is_torchvisions_centercrop():
+    """oracle.stitch's centred window == torchvision CenterCrop for every parity of (tile - crop), including the
+    round-half-to-even cases (utils.py:146,154)."""
+    import torch
+    import torchvision.transforms as T
+    for th, ch in [(8, 8), (9, 8), (10, 8), (11, 8), (12, 8), (13, 8), (15, 8), (40, 32), (39, 28), (35, 32)]:
+        tile = (torch.arange(th * th, dtype=torch.int64) % 251).to(torch.uint8).reshape(1, th, th)
+        want = T.CenterCrop(ch)(tile)[0].numpy()
+        got = c_oracle.stitch(tile.numpy(), np.array([[0, 0]], dtype=np.int32), ch, ch, crop=(ch, ch))
+        assert np.array_equal(got, want), (th, ch)
