@@ -81,7 +81,7 @@ class DirectoryScenes:
     def _open(path: str) -> torch.Tensor:
         import numpy as np
         from PIL import Image
-        a = np.asarray(Image.open(path))
+        a = np.array(Image.open(path))          # a writable copy (torch tensors must own writable memory)
         t = torch.from_numpy(np.ascontiguousarray(a))
         if t.dim() == 2:
             return t.unsqueeze(0)          # tv_tensors.Image / Mask of a single-band file: [1, H, W]

@@ -348,3 +348,36 @@ def test_c_abi_from_a_plain_c_host(tmp_path):
                     "-o", exe, "-ldl", "-lm"], check=True)
     r = subprocess.run([exe, _lib.LIB_PATH], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "C-ABI DEMO OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_converter_and_ensemble_dropins(golden):
+    """GID15Converter.iconvert (converters.py:23-36) and Ensemble.forward (utils.py:499-507) on the GPU vs the
+    reference-generated fixtures / torch.mode."""
+    from cvcs_b200.converters import GID15Converter
+    from cvcs_b200.ensemble import Ensemble
+    g = golden("misc_cases")
+    conv = GID15Converter()
+    assert np.array_equal((conv.lut("cpu")).numpy(), g["iconvert.lut"])
+    out = conv.iconvert(torch.from_numpy(g["iconvert.in"]))
+    assert not out.is_cuda and np.array_equal(out.numpy(), g["iconvert.out"])
+    out_d = conv.iconvert(torch.from_numpy(g["iconvert.in"]).to(torch.uint8).to(DEV))
+    assert out_d.is_cuda and np.array_equal(out_d.cpu().numpy(), g["iconvert.out"])
+
+    class Fixed(nn.Module):
+        def __init__(self, logits):
+            super().__init__()
+            self.logits = logits
+
+        def forward(self, x, context=None):
+            return self.logits
+
+    gen = torch.Generator().manual_seed(2)
+    members = [Fixed(torch.randn(1, 6, 24, 40, generator=gen).to(DEV)) for _ in range(4)]
+    ens = Ensemble(16, DEV, models=members)
+    assert ens.returns_logits is False and ens.requires_context is False
+    got = ens(torch.zeros(1, 3, 24, 40, device=DEV))
+    preds = [torch.argmax(m.logits.squeeze().permute(1, 2, 0).cpu(), dim=2) for m in members]      # utils.py:504
+    want, _ = torch.mode(torch.stack(tuple(preds), dim=0), dim=0)                                   # utils.py:506
+    assert got.shape == want.shape and torch.equal(got.cpu(), want)
+    with pytest.raises(Exception):
+        Ensemble(16, DEV, None)
