@@ -188,10 +188,9 @@ int launch_nchw(const CeParams& p, cudaStream_t stream) {
     constexpr int MINB = (C * VEC <= 32) ? 3 : (C * VEC <= 64 ? 2 : 1);
     auto kernel = ce_nchw_kernel<T, C, VEC, PRIV, MINB>;
     const int smem = p.confmat ? BinAcc<PRIV>::smem_bytes(C * C) : 0;
-    static int grid_cache[2] = {0, 0};  // [has confmat]
-    int& grid = grid_cache[p.confmat ? 1 : 0];
-    if (grid == 0) {
-        int rc = persistent_grid(kernel, kThreads, smem, &grid);
+    int grid = 0;
+    {
+        int rc = persistent_grid(kernel, kThreads, smem, &grid);  // cached per (kernel, smem, device)
         if (rc) return rc;
     }
     const long long blocks_needed = (p.n_items + kThreads - 1) / kThreads;
