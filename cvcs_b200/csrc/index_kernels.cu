@@ -502,6 +502,74 @@ __global__ void __launch_bounds__(kThreads) confmat_kernel(const ConfParams p) {
     if ((threadIdx.x & 31) == 0 && bad && p.status) atomicAdd(p.status, static_cast<unsigned long long>(bad));
 }
 
+// Both maps u8 and 16-byte aligned (the stored-mask / K2-output case): 16 pixels per 128-bit load, two loads
+// of each map in flight, and one +4 update for a word whose four (target, prediction) pairs agree — index
+// maps have long runs.
+template <bool PRIV>
+__global__ void __launch_bounds__(kThreads) confmat_u8_kernel(const ConfParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int C = p.C;
+    BinAcc<PRIV> acc;
+    acc.init(smem, C * C, p.reps, p.confmat);
+    unsigned int since_flush = 0, bad = 0;
+    const int ign = (p.ignore_index >= 0 && p.ignore_index <= 255) ? static_cast<int>(p.ignore_index) : -1;
+    auto one = [&](int t, int q, unsigned int n) {
+        if (t == ign) return;
+        if (t >= C || q >= C) {
+            bad += n;
+            return;
+        }
+        acc.add(t * C + q, n);
+    };
+    auto word = [&](uint32_t tw, uint32_t qw) {
+        const int t0 = static_cast<int>(tw & 0xff), q0 = static_cast<int>(qw & 0xff);
+        if (tw == static_cast<uint32_t>(t0) * 0x01010101u && qw == static_cast<uint32_t>(q0) * 0x01010101u) {
+            one(t0, q0, 4u);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) one(static_cast<int>((tw >> (8 * k)) & 0xff), static_cast<int>((qw >> (8 * k)) & 0xff), 1u);
+        }
+    };
+    const uint8_t* __restrict__ tgt = reinterpret_cast<const uint8_t*>(p.target);
+    const uint8_t* __restrict__ prd = reinterpret_cast<const uint8_t*>(p.pred);
+    const long long n16 = p.n / 16;
+    constexpr int U = 2;
+    const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+    for (long long base = static_cast<long long>(blockIdx.x) * kThreads; base < n16; base += U * stride) {
+        Raw<16> rt[U], rq[U];
+        bool have[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = base + u * stride + threadIdx.x;
+            have[u] = i < n16;
+            if (have[u]) {
+                rt[u].load(tgt + 16 * i);
+                rq[u].load(prd + 16 * i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!have[u]) continue;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) word(rt[u].word(k), rq[u].word(k));
+        }
+        if (PRIV) {
+            since_flush += 16 * U;
+            if (since_flush > 65535u - 16u * U) {
+                acc.flush(p.confmat);
+                since_flush = 0;
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        const long long i = n16 * 16 + threadIdx.x;
+        if (i < p.n) one(tgt[i], prd[i], 1u);
+    }
+    acc.flush(p.confmat);
+    bad = warp_sum(bad);
+    if ((threadIdx.x & 31) == 0 && bad && p.status) atomicAdd(p.status, static_cast<unsigned long long>(bad));
+}
+
 bool aligned_to(const void* q, size_t a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; }
 
 }  // namespace
@@ -666,6 +734,24 @@ int confmat_launch(const void* pred, int pred_dtype, const void* target, int tar
         if (rc) return rc;                                                              \
         confmat_kernel<PRIV, VEC><<<grid, kThreads, smem, stream>>>(p);                 \
     } while (0)
+    if (vec_ok && !p.pred_i64 && !p.target_i64) {
+        // u8 / u8: the fast kernel; at most 4 CTAs per SM (every CTA ends with one global atomic per bin)
+        const int smem = priv ? BinAcc<true>::smem_bytes(C * C) : BinAcc<false>::smem_bytes(C * C, p.reps);
+        long long blocks = (n / 32 + kThreads - 1) / kThreads;
+        const long long cap = 4ll * num_sms();
+        if (blocks > cap) blocks = cap;
+        if (priv) {
+            rc = grid_for(confmat_u8_kernel<true>, smem, blocks, &grid);
+            if (rc) return rc;
+            confmat_u8_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+        } else {
+            rc = grid_for(confmat_u8_kernel<false>, smem, blocks, &grid);
+            if (rc) return rc;
+            confmat_u8_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+        }
+        CVCS_CUDA_OK(cudaGetLastError());
+        return CVCS_OK;
+    }
     // 4 pixels per thread when both maps are u8 (32-bit loads) or any i64 (2 x 128-bit loads)
     if (vec_ok) {
         if (priv) CVCS_LAUNCH_CONF(true, 4);
