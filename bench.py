@@ -467,10 +467,14 @@ def main():
     sampler.stop()
     ms_total = start.elapsed_time(end)
     k1_ms = [a.elapsed_time(b) for a, b in k1_events]
+    per_rank = None
     if world > 1:
-        tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms_total = float(tmax.item())
+        # max over ranks of the device-timed region; the per-rank K1 averages say which GPU is the slow one
+        mine_t = torch.tensor([ms_total, sum(k1_ms) / max(len(k1_ms), 1)], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allt, mine_t)
+        ms_total = max(float(t_[0]) for t_ in allt)
+        per_rank = {"region_ms": [round(float(t_[0]), 3) for t_ in allt], "k1_avg_ms": [round(float(t_[1]), 4) for t_ in allt]}
     ms_per_step = ms_total / args.steps
     value = world * px_per_gpu / (ms_per_step * 1e-3) / 1e9
     gpu_launches = launches["n"]
@@ -552,7 +556,7 @@ def main():
                                       "one CxC confusion all-reduce per pass" if world > 1 else "single GPU",
                        "k4_prepass": "one step ahead on a side stream (overlaps K1)" if prepass_on else False, "path": args.path,
                        "sms_reserved_for_collectives": reserve},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "host_enqueue_ms_per_step": host_ms_per_step,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "host_enqueue_ms_per_step": host_ms_per_step, "per_rank": per_rank,
             "clocks": sampler.summary(),
             "check": {"confusion_total": total_cm, "loss": float(loss_out.item())},
         }
