@@ -449,9 +449,10 @@ def main():
     confmat.zero_()
     launches["n"] = 0
     issued["upto"] = -1
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local)          # NVML init takes milliseconds and differs per rank ...
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()                                # ... so line the ranks up again right before the timed region
+    sampler.start()
     start.record()
     host_t0 = time.perf_counter()
     for i in range(args.steps):
