@@ -372,6 +372,7 @@ def main():
     # prefetching loader), so the pre-pass — and at N > 1 its label-histogram all-reduce — overlaps K1.
     pre = torch.cuda.Stream(device=dev) if prepass_on else None
     tws = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(n_sets)]
+    t8s = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in range(n_sets)] if args.label_dtype == "i64" else None
     tw_sum = [t_[0:1] for t_ in tws]     # views made once: the per-step Python path is the bottleneck at N > 1
     tw_inv = [t_[1:2] for t_ in tws]
     pre_ready = [None] * n_sets      # event on `pre`: tws[j] holds this step's total weight
@@ -396,6 +397,10 @@ def main():
                 dist.all_reduce(tw_sum[j])                      # global Σw: every rank divides by the same total
                 torch.reciprocal(tw_sum[j], out=tw_inv[j])
                 launches["n"] += 1
+            elif t.dtype == torch.int64:
+                # the reference's .long() labels: one pass gives Σ v·w[y] and the byte labels K1 then reads
+                ops.labels_prepare(t, C, ii, weight, tws[j], t8s[j])
+                launches["n"] += 1
             else:
                 ops.label_hist(t, C, ii, weight=weight, total_weight_out=tws[j])
                 launches["n"] += 1
@@ -419,10 +424,13 @@ def main():
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        t_k1, ii_k1 = t, ii
+        if prepass_on and world == 1 and t.dtype == torch.int64:
+            t_k1, ii_k1 = t8s[j], 255                         # byte labels written by cvcs_labels_prepare
         if args.metrics_only:
             ops.eval_fused(x, t, ii, argmax=am[j], confmat=confmat)
         else:
-            ops.ce_fused(x, t, weight, ii, want_grad=grad, inv_total_weight=inv, inv_total_weight_dev=inv_dev,
+            ops.ce_fused(x, t_k1, weight, ii_k1, want_grad=grad, inv_total_weight=inv, inv_total_weight_dev=inv_dev,
                          dlogits=dl[j], argmax=am[j], confmat=confmat, loss_sums=sums_table[i % sums_rows], loss_out=loss_out)
         launches["n"] += 1
         if timed:

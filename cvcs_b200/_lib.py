@@ -50,6 +50,7 @@ SIGNATURES = {
     "cvcs_set_option": (_i, [_i, _i]),
     "cvcs_label_hist": (_i, [_vp, _i, _ll, _i, _ll, _vp, _vp, _vp, _vp, _vp]),
     "cvcs_total_weight": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
+    "cvcs_labels_prepare": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _vp, _vp, _vp]),
     "cvcs_ce_fused": (_i, [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _vp,
                            _vp, _vp, _vp]),
     "cvcs_eval_fused": (_i, [_vp, _i, _i, _vp, _i, _ll, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),

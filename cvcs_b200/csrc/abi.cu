@@ -42,6 +42,7 @@ int ce_fused_launch(const void*, int, int, const void*, int, const float*, long 
 int label_hist_launch(const void*, int, long long, int, long long, unsigned long long*, const float*, double*, void*,
                       cudaStream_t);
 int total_weight_launch(const unsigned long long*, const float*, int, long long, double*, cudaStream_t);
+int labels_prepare_launch(const long long*, long long, int, long long, const float*, double*, unsigned char*, void*, cudaStream_t);
 int scale_launch(void*, int, long long, const float*, cudaStream_t);
 int argmax_launch(const void*, int, int, int, int, int, int, void*, int, cudaStream_t);
 int confmat_launch(const void*, int, const void*, int, long long, int, long long, unsigned long long*,
@@ -118,6 +119,13 @@ int cvcs_label_hist(const void* target_dev, int target_dtype, long long n_pixels
                     void* workspace_dev, void* stream) {
     return label_hist_launch(target_dev, target_dtype, n_pixels, C, ignore_index, hist_dev, weight_dev,
                              total_weight_out_dev, workspace_dev, static_cast<cudaStream_t>(stream));
+}
+
+int cvcs_labels_prepare(const long long* target_dev, long long n_pixels, int C, long long ignore_index,
+                        const float* weight_dev, double* total_weight_out_dev, unsigned char* labels_u8_out_dev,
+                        void* workspace_dev, void* stream) {
+    return labels_prepare_launch(target_dev, n_pixels, C, ignore_index, weight_dev, total_weight_out_dev, labels_u8_out_dev,
+                                 workspace_dev, static_cast<cudaStream_t>(stream));
 }
 
 int cvcs_total_weight(const unsigned long long* hist_dev, const float* weight_dev, int C, long long ignore_index,

@@ -45,6 +45,7 @@ struct HistParams {
     long long ignore_index;
     int C;
     int target_i64;
+    unsigned char* narrow;  // nullable (i64 labels only): u8 copy of the labels, 255 = ignored, 254 = out of range
 };
 
 template <bool PRIV>
@@ -206,6 +207,10 @@ __global__ void __launch_bounds__(kThreads) weight_sum_kernel(const HistParams p
         const long long* __restrict__ tgt = reinterpret_cast<const long long*>(p.target);
         const long long n2 = p.n / 2;
         auto w_of = [&](long long v) { return (v >= 0 && v < C) ? lut[static_cast<int>(v)] : 0.f; };  // lut[ignore] == 0
+        // u8 code for K1: ignore_index -> 255, other values outside [0, C) -> 254 (counted as out of bounds there)
+        auto code_of = [&](long long v) -> unsigned int {
+            return v == p.ignore_index ? 255u : ((v >= 0 && v < C) ? static_cast<unsigned int>(v) : 254u);
+        };
         constexpr int U = 4;
         for (long long base = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; base < n2; base += U * stride) {
             Raw<16> r[U];
@@ -218,11 +223,20 @@ __global__ void __launch_bounds__(kThreads) weight_sum_kernel(const HistParams p
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (!have[u]) continue;
-                a[u & 3] += w_of((static_cast<long long>(r[u].v.y) << 32) | r[u].v.x);
-                a[(u + 2) & 3] += w_of((static_cast<long long>(r[u].v.w) << 32) | r[u].v.z);
+                const long long v0 = (static_cast<long long>(r[u].v.y) << 32) | r[u].v.x;
+                const long long v1 = (static_cast<long long>(r[u].v.w) << 32) | r[u].v.z;
+                a[u & 3] += w_of(v0);
+                a[(u + 2) & 3] += w_of(v1);
+                if (p.narrow) {
+                    const unsigned int c0 = code_of(v0), c1 = code_of(v1);
+                    __stcs(reinterpret_cast<unsigned short*>(p.narrow) + (base + u * stride), static_cast<unsigned short>(c0 | (c1 << 8)));
+                }
             }
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0 && (p.n & 1)) a[0] += w_of(tgt[p.n - 1]);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (p.n & 1)) {
+            a[0] += w_of(tgt[p.n - 1]);
+            if (p.narrow) p.narrow[p.n - 1] = static_cast<unsigned char>(code_of(tgt[p.n - 1]));
+        }
     }
     double s = static_cast<double>((a[0] + a[1]) + (a[2] + a[3]));
     s = warp_sum(s);
@@ -622,6 +636,31 @@ int label_hist_launch(const void* target, int target_dtype, long long n, int C, 
         if (rc) return rc;
         label_hist_kernel<false><<<grid, kThreads, smem, stream>>>(p);
     }
+    CVCS_CUDA_OK(cudaGetLastError());
+    return CVCS_OK;
+}
+
+int labels_prepare_launch(const long long* target, long long n, int C, long long ignore_index, const float* weight,
+                          double* tw_out, unsigned char* labels_u8, void* workspace, cudaStream_t stream) {
+    CVCS_REQUIRE((target || n == 0) && tw_out && (labels_u8 || n == 0) && workspace, "cvcs_labels_prepare: NULL argument");
+    CVCS_REQUIRE(n >= 0 && C >= 1 && C <= 254, "cvcs_labels_prepare: needs 1 <= C <= 254 (got %d)", C);
+    CVCS_REQUIRE(aligned_to(target, 16) && aligned_to(labels_u8, 2), "cvcs_labels_prepare: misaligned pointers");
+    HistParams p{};
+    p.target = target;
+    p.n = n;
+    p.weight = weight;
+    p.tw_out = tw_out;
+    p.ws = reinterpret_cast<Workspace*>(workspace);
+    p.ignore_index = ignore_index;
+    p.C = C;
+    p.target_i64 = 1;
+    p.narrow = labels_u8;
+    long long blocks = (n / 8 + kThreads - 1) / kThreads;
+    const long long cap = 8ll * num_sms();
+    if (blocks > cap) blocks = cap;
+    if (blocks > kMaxGrid) blocks = kMaxGrid;
+    if (blocks < 1) blocks = 1;
+    weight_sum_kernel<<<static_cast<int>(blocks), kThreads, 0, stream>>>(p);
     CVCS_CUDA_OK(cudaGetLastError());
     return CVCS_OK;
 }

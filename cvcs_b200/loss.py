@@ -127,13 +127,18 @@ class FusedCrossEntropyLoss(nn.Module):
             self._side = torch.cuda.Stream(device=dev)
         self._side.wait_stream(torch.cuda.current_stream(dev))     # the labels must have been produced
         tw = torch.empty(2, dtype=torch.float64, device=dev)
+        t8 = None
         with torch.cuda.stream(self._side):
-            ops.label_hist(t.contiguous(), num_classes, self.ignore_index, hist=None, weight=self._weight_f32(dev),
-                           total_weight_out=tw)
+            if t.dtype == torch.int64 and num_classes <= 254:
+                _, t8 = ops.labels_prepare(t.contiguous(), num_classes, self.ignore_index, self._weight_f32(dev), tw)
+                t8.record_stream(self._side)
+            else:
+                ops.label_hist(t.contiguous(), num_classes, self.ignore_index, hist=None, weight=self._weight_f32(dev),
+                               total_weight_out=tw)
             ev = torch.cuda.Event()
             ev.record(self._side)
         tw.record_stream(self._side)
-        self._prefetched = (target, num_classes, tw, ev)
+        self._prefetched = (target, num_classes, tw, ev, t8)
 
     def _run(self, logits: torch.Tensor, target: torch.Tensor, want_grad: bool):
         if not logits.is_cuda:
@@ -151,14 +156,22 @@ class FusedCrossEntropyLoss(nn.Module):
             raise RuntimeError(f"weight tensor should be defined either for all {C} classes or no classes "
                                f"but got weight tensor of shape: {list(w.shape)}")
         inv_tw, inv_tw_dev = 0.0, None
+        ii = self.ignore_index
         if want_grad:
             if w is None and t.dtype == torch.uint8 and not (0 <= self.ignore_index <= 255):
                 inv_tw = 1.0 / float(B * H * W)  # nothing can be ignored: Σ v·w is the pixel count
             elif self._prefetched is not None and self._prefetched[0] is target and self._prefetched[1] == C:
-                _, _, tw, ev = self._prefetched                   # pre-pass already running / done on the side stream
+                _, _, tw, ev, t8 = self._prefetched               # pre-pass already running / done on the side stream
                 torch.cuda.current_stream(dev).wait_event(ev)
                 inv_tw_dev = tw[1:]
+                if t8 is not None:
+                    t, ii = t8.reshape(t.shape), 255
                 self._prefetched = None
+            elif t.dtype == torch.int64 and C <= 254:
+                # the reference passes mask.type(torch.long): one pass over the 8-byte labels yields Σ v·w[y] AND a
+                # byte copy (255 = ignored, 254 = out of range) for the fused kernel to read instead
+                tw, t = ops.labels_prepare(t, C, self.ignore_index, w)
+                inv_tw_dev, ii = tw[1:], 255
             else:
                 tw = torch.empty(2, dtype=torch.float64, device=dev)
                 ops.label_hist(t, C, self.ignore_index, hist=None, weight=w, total_weight_out=tw)
@@ -167,7 +180,7 @@ class FusedCrossEntropyLoss(nn.Module):
         conf = None
         if self.confusion is not None:
             conf = self.confusion._state_for(dev, C)
-        loss_out, sums, dlogits = ops.ce_fused(x, t, w, self.ignore_index, want_grad=want_grad,
+        loss_out, sums, dlogits = ops.ce_fused(x, t, w, ii, want_grad=want_grad,
                                                inv_total_weight=inv_tw, inv_total_weight_dev=inv_tw_dev,
                                                argmax=argmax, confmat=conf)
         self.last_argmax = argmax

@@ -91,6 +91,25 @@ def label_hist(target: torch.Tensor, num_classes: int, ignore_index: int = -100,
     return hist
 
 
+def labels_prepare(target: torch.Tensor, num_classes: int, ignore_index: int = -100,
+                   weight: Optional[torch.Tensor] = None, total_weight_out: Optional[torch.Tensor] = None,
+                   labels_u8_out: Optional[torch.Tensor] = None):
+    """int64 labels -> (f64[2] {Σ v·w[y], 1/Σ}, u8 labels with 255 = ignored / 254 = out of range) in one pass."""
+    dev = _need_cuda(target, weight, total_weight_out, labels_u8_out)
+    if target.dtype != torch.int64:
+        raise RuntimeError(f"labels_prepare expects int64 labels, got {target.dtype}")
+    target = target.contiguous()
+    if total_weight_out is None:
+        total_weight_out = torch.empty(2, dtype=torch.float64, device=dev)
+    if labels_u8_out is None:
+        labels_u8_out = torch.empty(target.shape, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.cvcs_labels_prepare(target.data_ptr(), target.numel(), num_classes, ignore_index, _ptr(weight),
+                                      total_weight_out.data_ptr(), labels_u8_out.data_ptr(), workspace(dev).data_ptr(),
+                                      _stream(dev)))
+    return total_weight_out, labels_u8_out
+
+
 def total_weight(hist: torch.Tensor, weight: Optional[torch.Tensor], num_classes: int, ignore_index: int,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     dev = _need_cuda(hist, weight, out)

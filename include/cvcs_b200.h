@@ -7,6 +7,7 @@
  *
  *   cvcs_label_hist       <- Loader._get_class_count            dataset.py:346-358
  *   cvcs_total_weight     <- the "mean" divisor of nn.CrossEntropyLoss (utils.py:230,238)
+ *   cvcs_labels_prepare   <- mask.type(torch.long) + that divisor          train.py:122
  *   cvcs_ce_fused         <- crit(mask_pred, mask.long())       train.py:122, utils.py:120
  *                            loss.backward()                    train.py:125
  *                            torch.max(y_pred, dim=0)           utils.py:90
@@ -111,6 +112,14 @@ int cvcs_set_option(int option, int value);
 int cvcs_label_hist(const void* target_dev, int target_dtype, long long n_pixels, int C,
                     long long ignore_index, unsigned long long* hist_dev, const float* weight_dev,
                     double* total_weight_out_dev, void* workspace_dev, void* stream);
+
+/* int64 labels (what the reference passes: mask.type(torch.long), train.py:122) in ONE pass over them:
+ * total_weight_out_dev f64[2] = {Σ_i v_i w[y_i], 1/Σ} as above, and labels_u8_out_dev[i] = the label as a
+ * byte (ignore_index -> 255, any other value outside [0, C) -> 254), so that K1 reads 1 B/px instead of
+ * 8 B/px: call cvcs_ce_fused with target_dtype CVCS_U8 and ignore_index 255 afterwards.  Needs C <= 254. */
+int cvcs_labels_prepare(const long long* target_dev, long long n_pixels, int C, long long ignore_index,
+                        const float* weight_dev, double* total_weight_out_dev,
+                        unsigned char* labels_u8_out_dev, void* workspace_dev, void* stream);
 
 /* Σ_i v_i w[y_i] from a label histogram (e.g. after an all-reduce across ranks):
  * out_dev[0] = Σw (f64), out_dev[1] = 1/Σw.  weight_dev nullable (all ones).  Class

@@ -281,3 +281,26 @@ def test_eval_fused_metrics_mode(layout, dtype, label_dtype, C, H, W):
     am64 = torch.empty((B, H, W), dtype=torch.int64, device=DEV)
     ops.eval_fused(xd, td, None, argmax=am64)
     assert np.array_equal(am64.cpu().numpy(), am_ref)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 4096, 100003])
+@pytest.mark.parametrize("C,ignore", [(7, 255), (7, 0), (16, -100), (254, 3)])
+def test_labels_prepare_i64(n, C, ignore):
+    """cvcs_labels_prepare: int64 labels -> {Σ v·w[y], 1/Σ} and the byte labels K1 reads (255 ignored, 254 out of range)."""
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(n + C)
+    t = torch.randint(0, C, (n,), generator=g, dtype=torch.int64)
+    if n >= 7:
+        t[1] = ignore
+        t[2] = C + 5            # out of range
+        t[3] = -7               # out of range (negative), unless it is the ignore value
+        t[5] = 1 << 40          # out of range, does not fit 32 bits
+    w = torch.rand(C, generator=g) + 0.5
+    tw, t8 = ops.labels_prepare(t.to(DEV), C, ignore, w.to(DEV))
+    tn = t.numpy()
+    valid = (tn >= 0) & (tn < C) & (tn != ignore)
+    want = np.where(tn == ignore, 255, np.where((tn >= 0) & (tn < C), tn, 254)).astype(np.uint8)
+    assert np.array_equal(t8.cpu().numpy(), want)
+    sw = float(w.double().numpy()[tn[valid]].sum()) if n else 0.0
+    if sw > 0:
+        assert abs(float(tw[0]) - sw) <= 1e-6 * sw and abs(float(tw[1]) * sw - 1.0) <= 1e-6
