@@ -176,7 +176,7 @@ def cpu_reference_rate(wl, steps, warmup, budget_s, log=None):
     per_px = min(one(x, t, w) for _ in range(2)) / (128 * W)
     px_budget = budget_s / max(steps + warmup, 1) / per_px
     rows = int(min(wl["H"], max(32, (px_budget // W) // 32 * 32)))
-    tiles = int(min(2, max(1, px_budget // (rows * W)))) if rows == wl["H"] else 1
+    tiles = int(min(wl["B"], max(1, px_budget // (rows * W)))) if rows == wl["H"] else 1   # up to the full per-GPU batch
     x, t, w = make(rows, tiles)
     for _ in range(warmup):
         one(x, t, w)
