@@ -7,7 +7,7 @@ cp gpurun_out/bench_default.log profiles/$TAG/bench_default.json
 cp gpurun_out/bench_reference.log profiles/$TAG/bench_reference.json
 cp gpurun_out/bench_variants.log profiles/$TAG/bench_variants.jsonl
 cp gpurun_out/kernel_bench.jsonl profiles/$TAG/ 2>/dev/null
-for f in gpurun_out/prof_*.details.txt; do
+for f in gpurun_out/prof_*.details.txt; do   # NOTE: clean the local gpurun_out/ first — gpurun merges, it does not mirror
   n=$(basename $f .details.txt); n=${n#prof_}
   cp gpurun_out/prof_$n.details.txt gpurun_out/prof_$n.source.csv.gz profiles/$TAG/
   python - "$n" "$TAG" <<'PY'
