@@ -170,9 +170,10 @@ __device__ __forceinline__ void softmax_core(float (&x)[C], float& m, float& s, 
     arg = C - 1;
 #pragma unroll
     for (int c = C - 2; c >= 0; --c) arg = (x[c] == m) ? c : arg;
-    s = 0.f;
+    x[0] = exp_shifted<FUSED>(x[0], m);
+    s = x[0];                     // same bits as 0 + e0 (e0 >= +0), one FADD fewer per pixel
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
+    for (int c = 1; c < C; ++c) {
         x[c] = exp_shifted<FUSED>(x[c], m);
         s += x[c];
     }

@@ -63,6 +63,8 @@ class _FusedCE(torch.autograd.Function):
             raise RuntimeError("FusedCrossEntropyLoss: backward called but the forward ran without grad")
         ctx.dlogits = None
         mode = ctx.module.grad_scale_mode
+        if mode == "check" and torch.cuda.is_current_stream_capturing():
+            mode = "scale"            # no host read inside a CUDA-graph capture: multiply on the device instead
         if mode == "check":
             # `loss.backward()` feeds exactly 1.0 (train.py:125); the reference loop has already
             # synchronised on loss.item(), so reading 4 bytes here costs no extra bubble.

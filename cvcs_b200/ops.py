@@ -22,6 +22,7 @@ _DTYPE_TAG = {
 }
 
 _workspaces: dict = {}
+_capture_workspaces: list = []   # see workspace()
 
 
 def _tag(t: torch.Tensor) -> int:
@@ -55,7 +56,16 @@ def _stream(dev: torch.device) -> int:
 
 
 def workspace(dev: torch.device) -> torch.Tensor:
-    """Zero-initialised scratch buffer, one per (device, stream); kernels leave it zeroed."""
+    """Zero-initialised scratch buffer, one per (device, stream); kernels leave it zeroed.
+
+    While the current stream is being captured into a CUDA graph the buffer comes from the graph's own memory pool
+    (its zeroing becomes a memset node, so every replay starts from zeros) and is kept alive for the life of the
+    process instead of being cached per stream: the capture stream is reused by later captures, whose kernels must
+    not inherit a buffer that belongs to an earlier, possibly destroyed, graph."""
+    if torch.cuda.is_current_stream_capturing():
+        ws = torch.zeros(_lib.workspace_bytes(), dtype=torch.uint8, device=dev)
+        _capture_workspaces.append(ws)
+        return ws
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev))
     ws = _workspaces.get(key)
     if ws is None:
