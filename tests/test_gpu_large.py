@@ -93,3 +93,50 @@ def test_batches_beyond_2_31(B, C, dtype, layout):
     assert gmax > 0.0
     del x, d, t, am, am2
     torch.cuda.empty_cache()
+
+
+def test_tiler_scene_beyond_2_31_bytes():
+    """K5 on a 13-band scene of 2.2e9 bytes (source offsets past 2^31): every grid tile against torch's own slicing +
+    (v - mean) / std on the device (IEEE fp32, the same arithmetic), and the tiles of the last rows / columns plus an
+    overhanging one against the oracle run on the scene's bottom-right corner (dataset.py:29-31, nets.py:339-342)."""
+    import numpy as np
+    from cvcs_b200 import ops
+    from oracle import c_oracle
+    Cb, H, W, p = 13, 13056, 13056, 512
+    free, _ = torch.cuda.mem_get_info(DEV)
+    if free < 60 * 2 ** 30:
+        pytest.skip("needs 60 GB of free device memory")
+    torch.manual_seed(9)
+    scene = torch.empty((Cb, H, W), dtype=torch.uint8, device=DEV)
+    for c in range(Cb):
+        scene[c] = torch.randint(0, 256, (H, W), dtype=torch.uint8, device=DEV)
+    assert scene.numel() > 2 ** 31
+    lab = torch.randint(0, 16, (H, W), dtype=torch.uint8, device=DEV)
+    mean = torch.rand(Cb, device=DEV) * 100
+    std = torch.rand(Cb, device=DEV) * 50 + 1
+    rows, cols = H // p, W // p
+    grid = [(r * p, c * p) for r in range(rows) for c in range(cols)]
+    extra = [(H - p // 2, W - p // 2), (H - p, W - p - 3), (H - p - 7, W - p)]            # overhanging / unaligned, far corner
+    yx = torch.tensor(grid + extra, dtype=torch.int32, device=DEV)
+    hist = torch.zeros(18, dtype=torch.int64, device=DEV)
+    out, lo = ops.tile_normalize(scene, yx, (p, p), mean, std, label=lab, hist=hist, hist_classes=16)
+    torch.cuda.synchronize()
+    n = len(grid)
+    ref_u8 = scene[:, :rows * p, :cols * p].reshape(Cb, rows, p, cols, p).permute(1, 3, 0, 2, 4).reshape(n, Cb, p, p)
+    ref = (ref_u8.float() - mean[None, :, None, None]) / std[None, :, None, None]
+    assert torch.equal(out[:n], ref)
+    del ref, ref_u8
+    ref_lab = lab[:rows * p, :cols * p].reshape(rows, p, cols, p).permute(0, 2, 1, 3).reshape(n, p, p)
+    assert torch.equal(lo[:n], ref_lab)
+    # the far corner on the host: a 1536-pixel square holds the last grid tile and the three extra ones
+    k = 1536
+    sub = scene[:, H - k:, W - k:].cpu().numpy()
+    sub_lab = lab[H - k:, W - k:].cpu().numpy()
+    sel = [n - 1, n, n + 1, n + 2]
+    yx_sub = (yx[sel].cpu().numpy() - np.array([[H - k, W - k]], dtype=np.int32)).astype(np.int32)
+    assert yx_sub.min() >= 0
+    r, rl = c_oracle.tile(sub, yx_sub, p, p, mean.cpu().numpy(), std.cpu().numpy(), labels=sub_lab)
+    assert np.array_equal(out[sel].cpu().numpy(), r)
+    assert np.array_equal(lo[sel].cpu().numpy(), rl)
+    # label histogram of all gathered tiles (K5's fused class count, dataset.py:360-384)
+    assert torch.equal(hist[:16], torch.bincount(lo.flatten().long(), minlength=16)[:16])
