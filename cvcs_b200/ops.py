@@ -6,6 +6,7 @@ libcvcs_b200.so.  CPU tensors are rejected: there is no CPU path.
 from __future__ import annotations
 
 import ctypes
+import collections
 from typing import Optional, Tuple
 
 import torch
@@ -22,7 +23,7 @@ _DTYPE_TAG = {
 }
 
 _workspaces: dict = {}
-_capture_workspaces: list = []   # see workspace()
+_capture_workspaces: collections.deque = collections.deque(maxlen=1024)   # see workspace()
 
 
 def _tag(t: torch.Tensor) -> int:
@@ -59,8 +60,8 @@ def workspace(dev: torch.device) -> torch.Tensor:
     """Zero-initialised scratch buffer, one per (device, stream); kernels leave it zeroed.
 
     While the current stream is being captured into a CUDA graph the buffer comes from the graph's own memory pool
-    (its zeroing becomes a memset node, so every replay starts from zeros) and is kept alive for the life of the
-    process instead of being cached per stream: the capture stream is reused by later captures, whose kernels must
+    (its zeroing becomes a memset node, so every replay starts from zeros) and is kept alive (the last 1024 of them,
+    128 KB each) instead of being cached per stream: the capture stream is reused by later captures, whose kernels must
     not inherit a buffer that belongs to an earlier, possibly destroyed, graph."""
     if torch.cuda.is_current_stream_capturing():
         ws = torch.zeros(_lib.workspace_bytes(), dtype=torch.uint8, device=dev)
