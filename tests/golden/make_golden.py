@@ -14,6 +14,7 @@ oracle/ref_shim.py) or from the torch / torchvision call the cited reference lin
   eval_cases.npz     utils.eval_model(fake net, fake loader) (utils.py:59-103) -> flat/normalised
                      matrices, utils.print_metrics (utils.py:375-403)
   metrics_cases.npz  IoU/F1/precision/recall/accuracy on hand-made matrices (utils.py:301-373)
+  metrics_random.npz the same functions + print_metrics on 24 seeded random matrices
   dataset_cases.npz  dataset.Loader on a tiny on-disk GID-like tree: tile order, crops, class
                      counts and weights (dataset.py:28-32,105-221,241-384); crop helpers with
                      out-of-bounds offsets (dataset.py:11-32); Normalize (nets.py:339-342)
@@ -210,6 +211,40 @@ def metrics_cases():
     np.savez_compressed(os.path.join(HERE, "metrics_cases.npz"), **out)
 
 
+def metrics_random_cases(n=24):
+    """Seeded random confusion matrices (2..16 classes, empty rows / columns, counts up to 2^36) through the
+    reference's IoU / F1 / precision / recall / accuracy and print_metrics (utils.py:301-403)."""
+    out = {}
+    g = torch.Generator().manual_seed(17)
+    for i in range(n):
+        C = int(torch.randint(2, 17, (1,), generator=g))
+        hi = int(2 ** int(torch.randint(3, 37, (1,), generator=g)))
+        cm = torch.randint(0, hi, (C, C), generator=g)
+        for axis in (0, 1):                                  # knock out some rows / columns (absent classes)
+            dead = torch.rand(C, generator=g) < 0.2
+            if axis == 0:
+                cm[dead, :] = 0
+            else:
+                cm[:, dead] = 0
+        if i % 6 == 0:
+            cm[0, :] = 0                                     # the ignore_background shape: row 0 empty
+        out[f"r{i}.cm"] = cm.numpy().astype(np.int64)
+        for kind, fn, kw in (("iou", utils.IoU, "mean"), ("f1", utils.F1, "mean"),
+                             ("precision", utils.precision, "macro"), ("recall", utils.recall, "macro")):
+            scores, excluded = fn(cm, **{kw: False}, return_excluded=True)
+            out[f"r{i}.{kind}.scores"] = scores.numpy()
+            out[f"r{i}.{kind}.excluded"] = np.array(excluded, dtype=np.int64)
+            out[f"r{i}.{kind}.mean"] = np.float64(fn(cm, **{kw: True}))
+        out[f"r{i}.accuracy"] = np.float64(utils.accuracy(cm))
+        if cm.sum() > 0:
+            m = utils.print_metrics(cm, silent=True)
+            out[f"r{i}.print.keys"] = np.array(sorted(m.keys()))
+            for k, v in m.items():
+                out[f"r{i}.print.{k}"] = np.asarray(v, dtype=np.float64)
+    out["n"] = np.int64(n)
+    np.savez_compressed(os.path.join(HERE, "metrics_random.npz"), **out)
+
+
 def dataset_cases():
     from PIL import Image
     out = {}
@@ -291,6 +326,7 @@ if __name__ == "__main__":
     argmax_cases()
     eval_cases()
     metrics_cases()
+    metrics_random_cases()
     dataset_cases()
     misc_cases()
     manifest = {
