@@ -15,6 +15,7 @@ oracle/ref_shim.py) or from the torch / torchvision call the cited reference lin
                      matrices, utils.print_metrics (utils.py:375-403)
   metrics_cases.npz  IoU/F1/precision/recall/accuracy on hand-made matrices (utils.py:301-373)
   metrics_random.npz the same functions + print_metrics on 24 seeded random matrices
+  weight_cases.npz   Loader.get_class_weights on 16 seeded random class-count vectors (dataset.py:360-384)
   dataset_cases.npz  dataset.Loader on a tiny on-disk GID-like tree: tile order, crops, class
                      counts and weights (dataset.py:28-32,105-221,241-384); crop helpers with
                      out-of-bounds offsets (dataset.py:11-32); Normalize (nets.py:339-342)
@@ -245,6 +246,35 @@ def metrics_random_cases(n=24):
     np.savez_compressed(os.path.join(HERE, "metrics_random.npz"), **out)
 
 
+def weight_cases(n=16):
+    """dataset.Loader.get_class_weights (dataset.py:360-384) on seeded random class counts: empty classes, huge and
+    tiny counts, with and without ignore_background."""
+    class CountsOnly:
+        def __init__(self, counts):
+            self.counts = counts
+
+        get_class_weights = dataset.Loader.get_class_weights
+
+        def _get_class_count(self, classes):
+            return self.counts
+
+    out = {}
+    g = torch.Generator().manual_seed(23)
+    for i in range(n):
+        C = int(torch.randint(2, 21, (1,), generator=g))
+        hi = int(2 ** int(torch.randint(2, 34, (1,), generator=g)))
+        counts = torch.randint(0, hi, (C,), generator=g).to(torch.float32)     # _get_class_count returns float32
+        counts[torch.rand(C, generator=g) < 0.25] = 0
+        if i == 0:
+            counts[:] = 0
+            counts[1] = 5
+        out[f"w{i}.counts"] = counts.numpy()
+        for ib in (False, True):
+            out[f"w{i}.ib{int(ib)}"] = CountsOnly(counts.clone()).get_class_weights(C, ib).numpy()
+    out["n"] = np.int64(n)
+    np.savez_compressed(os.path.join(HERE, "weight_cases.npz"), **out)
+
+
 def dataset_cases():
     from PIL import Image
     out = {}
@@ -327,6 +357,7 @@ if __name__ == "__main__":
     eval_cases()
     metrics_cases()
     metrics_random_cases()
+    weight_cases()
     dataset_cases()
     misc_cases()
     manifest = {
@@ -334,6 +365,7 @@ if __name__ == "__main__":
         "reference": "theElandor/CVCS @ /root/reference (unmodified, imported via oracle/ref_shim.py)",
         "torch": torch.__version__,
         "ce_case_names": names,
+        "files": sorted(f for f in os.listdir(HERE) if f.endswith(".npz")),
     }
     with open(os.path.join(HERE, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)
