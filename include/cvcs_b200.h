@@ -86,6 +86,10 @@ int cvcs_sm_count(void);
  * allocation; kernels leave it zeroed again on exit. */
 size_t cvcs_workspace_bytes(void);
 
+/* Sizes: every index on the path is 64-bit.  Entry points accept up to 2^33 pixels per call (B*H*W, or n for the
+ * index-map kernels) and any scene size; tests/test_gpu_large.py runs batches of 2.2e9 pixels / 4.4e9 logit elements
+ * and a scene of 2.2e9 bytes.  Larger inputs are refused with CVCS_ERR_INVALID_ARG ("too many pixels"). */
+
 /* Process-wide tuning knobs (A/B measurements, path-coverage tests).  Every value selects
  * among CUDA implementations of the same entry point; none changes results. */
 enum cvcs_option {
