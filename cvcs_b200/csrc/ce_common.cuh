@@ -133,6 +133,19 @@ __device__ __forceinline__ float rcp_ftz(float x) {
     return y;
 }
 
+#ifdef CVCS_X_PACKED_ARGMAX
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_eq_mask(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("set.eq.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));   // 0xffff per half where equal
+    return d;
+}
+#endif
+
 // torch.max over one pixel's classes with its NaN rule, from a fetch functor (slow path only).
 template <int C, typename F>
 __device__ __forceinline__ int argmax_nan_aware(F&& fetch) {

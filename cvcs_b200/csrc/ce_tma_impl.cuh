@@ -382,6 +382,22 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                 for (int k0 = 0; k0 < VECP; k0 += PP) {
                     float x[PP][C];
                     float r[PP];
+#ifdef CVCS_X_PACKED_ARGMAX
+                    // experiment: max and first-max index of the pixel pair on the packed bf16 words (max.bf16x2 +
+                    // set.eq.bf16x2 masks + one LOP3 per class) instead of per pixel in fp32
+                    [[maybe_unused]] uint32_t m2 = 0u, arg2 = 0u;
+                    if constexpr (ES == 2 && PP == 2 && !NHWC && LOSS) {
+                        m2 = raw[ridx(0, k0) >> 1];
+#pragma unroll
+                        for (int c = 1; c < C; ++c) m2 = bf16x2_max(m2, raw[ridx(c, k0) >> 1]);
+                        arg2 = static_cast<uint32_t>(C - 1) * 0x00010001u;
+#pragma unroll
+                        for (int c = C - 2; c >= 0; --c) {
+                            const uint32_t hit = bf16x2_eq_mask(raw[ridx(c, k0) >> 1], m2);
+                            arg2 = arg2 ^ ((arg2 ^ (static_cast<uint32_t>(c) * 0x00010001u)) & hit);
+                        }
+                    }
+#endif
 #pragma unroll
                     for (int q = 0; q < PP; ++q) {
                         const int k = k0 + q;
@@ -400,6 +416,19 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                         float m, s;
                         int arg;
                         if constexpr (LOSS) {
+#ifdef CVCS_X_PACKED_ARGMAX
+                            if constexpr (ES == 2 && PP == 2 && !NHWC) {
+                                m = q ? bf16_hi(m2) : bf16_lo(m2);
+                                arg = static_cast<int>(q ? (arg2 >> 16) : (arg2 & 0xffffu));
+                                x[q][0] = exp_shifted<true>(x[q][0], m);
+                                s = x[q][0];
+#pragma unroll
+                                for (int c = 1; c < C; ++c) {
+                                    x[q][c] = exp_shifted<true>(x[q][c], m);
+                                    s += x[q][c];
+                                }
+                            } else
+#endif
                             softmax_core<C, ES == 2>(x[q], m, s, arg);
                         } else {
                             // metrics mode: only the argmax is wanted.  Σ x is NaN exactly when the row holds a NaN

@@ -34,13 +34,13 @@ def kernel_instructions(lib, key):
 
 def fast_path(ins):
     addr = {a: i for i, (a, _) in enumerate(ins)}
-    is_work = lambda t: "FMNMX" in t or "MUFU.EX2" in t
+    is_work = lambda t: "MNMX" in t or "MUFU.EX2" in t
     loops = []
     for i, (a, t) in enumerate(ins):
         m = re.match(r"BRA (0x[0-9a-f]+)", t)
         if m and int(m.group(1), 16) < a and int(m.group(1), 16) in addr:
             head = addr[int(m.group(1), 16)]
-            if any("FMNMX" in ins[j][1] for j in range(head, i)):
+            if any("MNMX" in ins[j][1] for j in range(head, i)):
                 loops.append((head, i))
     head, tail = min(loops, key=lambda c: c[1] - c[0])
     pc, n, ops = head, 0, {}
