@@ -53,4 +53,5 @@ def test_library_has_no_torch_dependency():
     import subprocess
     from cvcs_b200 import _lib
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    assert "torch" not in out and "c10" not in out
+    names = [line.split()[0] for line in out.splitlines() if line.strip()]      # library names only: the load
+    assert names and not any("torch" in n or "c10" in n for n in names)         # addresses are random hex ("...c10...")
