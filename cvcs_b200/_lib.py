@@ -53,6 +53,16 @@ SIGNATURES = {
     "cvcs_labels_prepare": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _vp, _vp, _vp]),
     "cvcs_ce_fused": (_i, [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _vp,
                            _vp, _vp, _vp]),
+    "cvcs_ce_fused_tw": (_i, [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp,
+                              _vp, _vp, _vp]),
+    "cvcs_xchg_create": (_i, [C.POINTER(_vp), _i, _i]),
+    "cvcs_xchg_local_handle": (_i, [_vp, _vp]),
+    "cvcs_xchg_open_peer": (_i, [_vp, _i, _vp]),
+    "cvcs_xchg_set_peer": (_i, [_vp, _i, _vp]),
+    "cvcs_xchg_local_block": (_vp, [_vp]),
+    "cvcs_xchg_state": (_i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+    "cvcs_xchg_poke": (_i, [_vp, _i, C.c_ulonglong, _d, _vp]),
+    "cvcs_xchg_destroy": (_i, [_vp]),
     "cvcs_eval_fused": (_i, [_vp, _i, _i, _vp, _i, _ll, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "cvcs_scale_inplace": (_i, [_vp, _i, _ll, _vp, _vp]),
     "cvcs_argmax": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
@@ -84,7 +94,7 @@ def check(code: int) -> None:
         raise CvcsError(code, last_error())
 
 
-OPT_CE_PATH, OPT_TMA_STAGES, OPT_TMA_WAIT_HINT, OPT_TMA_VECP, OPT_TMA_CTAS, OPT_TILE_CTAS, OPT_RESERVE_SMS = 0, 1, 2, 3, 4, 5, 6
+OPT_CE_PATH, OPT_TMA_STAGES, OPT_TMA_WAIT_HINT, OPT_TMA_VECP, OPT_TMA_CTAS, OPT_TILE_CTAS, OPT_RESERVE_SMS, OPT_PDL = 0, 1, 2, 3, 4, 5, 6, 7
 CE_PATH_AUTO, CE_PATH_TMA, CE_PATH_DIRECT, CE_PATH_GENERIC = 0, 1, 2, 3
 
 

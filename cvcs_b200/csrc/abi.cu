@@ -6,7 +6,7 @@
 
 #include <vector>
 
-#include "common.cuh"
+#include "ce_common.cuh"
 
 namespace cvcs {
 
@@ -38,7 +38,7 @@ int num_sms() {
 // launchers implemented in the kernel translation units
 int ce_fused_launch(const void*, int, int, const void*, int, const float*, long long, int, int, int, int, double,
                     const double*, void*, void*, int, unsigned long long*, double*, float*, void*, cudaStream_t,
-                    unsigned long long* status = nullptr, int no_loss = 0);
+                    unsigned long long* status = nullptr, int no_loss = 0, const TwRequest* tw = nullptr);
 int label_hist_launch(const void*, int, long long, int, long long, unsigned long long*, const float*, double*, void*,
                       cudaStream_t);
 int total_weight_launch(const unsigned long long*, const float*, int, long long, double*, cudaStream_t);
@@ -141,6 +141,118 @@ int cvcs_ce_fused(const void* logits_dev, int logits_dtype, int layout, const vo
     return ce_fused_launch(logits_dev, logits_dtype, layout, target_dev, target_dtype, weight_dev, ignore_index, B, C, H,
                            W, inv_total_weight, inv_total_weight_dev, dlogits_dev, argmax_dev, argmax_dtype, confmat_dev,
                            loss_sums_dev, loss_out_dev, workspace_dev, static_cast<cudaStream_t>(stream));
+}
+
+// ---- Σw exchange handle: the local block + the peers' blocks mapped through CUDA IPC ------------------------------
+struct cvcs_xchg {
+    int world, rank, device;
+    XchgBlock* peer[kXMaxRanks];
+    bool opened[kXMaxRanks];      // mapped with cudaIpcOpenMemHandle (to be closed), as opposed to set directly
+};
+
+int cvcs_xchg_create(cvcs_xchg** out, int world, int rank) {
+    CVCS_REQUIRE(out && world >= 1 && world <= kXMaxRanks && rank >= 0 && rank < world, "cvcs_xchg_create: world %d rank %d (max %d ranks)",
+                 world, rank, kXMaxRanks);
+    *out = nullptr;
+    cvcs_xchg* x = new cvcs_xchg();
+    x->world = world;
+    x->rank = rank;
+    for (int q = 0; q < kXMaxRanks; ++q) { x->peer[q] = nullptr; x->opened[q] = false; }
+    cudaError_t e = cudaGetDevice(&x->device);
+    void* blk = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&blk, sizeof(XchgBlock));     // its own allocation: an IPC handle maps whole allocations
+    if (e == cudaSuccess) e = cudaMemset(blk, 0, sizeof(XchgBlock));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        if (blk) cudaFree(blk);
+        delete x;
+        (void)cudaGetLastError();
+        return set_error(CVCS_ERR_CUDA, "cvcs_xchg_create: %s", cudaGetErrorString(e));
+    }
+    x->peer[rank] = static_cast<XchgBlock*>(blk);
+    *out = x;
+    return CVCS_OK;
+}
+
+int cvcs_xchg_local_handle(cvcs_xchg* x, unsigned char* handle_out64) {
+    CVCS_REQUIRE(x && handle_out64, "cvcs_xchg_local_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CVCS_CUDA_OK(cudaIpcGetMemHandle(&h, x->peer[x->rank]));
+    memcpy(handle_out64, &h, 64);
+    return CVCS_OK;
+}
+
+int cvcs_xchg_open_peer(cvcs_xchg* x, int peer_rank, const unsigned char* handle64) {
+    CVCS_REQUIRE(x && handle64 && peer_rank >= 0 && peer_rank < x->world && peer_rank != x->rank, "cvcs_xchg_open_peer: bad peer rank %d", peer_rank);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* ptr = nullptr;
+    CVCS_CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    x->peer[peer_rank] = static_cast<XchgBlock*>(ptr);
+    x->opened[peer_rank] = true;
+    return CVCS_OK;
+}
+
+int cvcs_xchg_set_peer(cvcs_xchg* x, int peer_rank, void* block_dev) {
+    CVCS_REQUIRE(x && block_dev && peer_rank >= 0 && peer_rank < x->world && peer_rank != x->rank, "cvcs_xchg_set_peer: bad peer rank %d", peer_rank);
+    x->peer[peer_rank] = static_cast<XchgBlock*>(block_dev);
+    x->opened[peer_rank] = false;
+    return CVCS_OK;
+}
+
+void* cvcs_xchg_local_block(cvcs_xchg* x) { return x ? x->peer[x->rank] : nullptr; }
+
+int cvcs_xchg_state(cvcs_xchg* x, unsigned long long* seq_out, unsigned long long* errors_out) {
+    CVCS_REQUIRE(x, "cvcs_xchg_state: NULL handle");
+    XchgBlock* b = x->peer[x->rank];
+    if (seq_out) CVCS_CUDA_OK(cudaMemcpy(seq_out, &b->seq, 8, cudaMemcpyDeviceToHost));
+    if (errors_out) CVCS_CUDA_OK(cudaMemcpy(errors_out, &b->errors, 8, cudaMemcpyDeviceToHost));
+    return CVCS_OK;
+}
+
+int cvcs_xchg_poke(cvcs_xchg* x, int as_rank, unsigned long long seq, double value, void* stream) {
+    CVCS_REQUIRE(x && as_rank >= 0 && as_rank < x->world && seq > 0, "cvcs_xchg_poke: bad argument");
+    XchgBlock* b = x->peer[x->rank];
+    const int slot = static_cast<int>(seq % kXDepth);
+    const unsigned int tag = static_cast<unsigned int>(seq);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CVCS_CUDA_OK(cudaMemcpyAsync(&b->slots[slot][as_rank], &value, 8, cudaMemcpyHostToDevice, st));
+    CVCS_CUDA_OK(cudaMemcpyAsync(&b->flags[slot][as_rank], &tag, 4, cudaMemcpyHostToDevice, st));
+    CVCS_CUDA_OK(cudaStreamSynchronize(st));     // the host values above live on this stack frame
+    return CVCS_OK;
+}
+
+int cvcs_xchg_destroy(cvcs_xchg* x) {
+    if (!x) return CVCS_OK;
+    for (int q = 0; q < x->world; ++q)
+        if (q != x->rank && x->opened[q] && x->peer[q]) cudaIpcCloseMemHandle(x->peer[q]);
+    if (x->peer[x->rank]) cudaFree(x->peer[x->rank]);
+    (void)cudaGetLastError();
+    delete x;
+    return CVCS_OK;
+}
+
+int cvcs_ce_fused_tw(const void* logits_dev, int logits_dtype, int layout, const void* target_dev, int target_dtype,
+                     const float* weight_dev, long long ignore_index, int B, int C, int H, int W, cvcs_xchg* xchg,
+                     double* total_weight_out_dev, void* dlogits_dev, void* argmax_dev, int argmax_dtype,
+                     unsigned long long* confmat_dev, double* loss_sums_dev, float* loss_out_dev, void* workspace_dev,
+                     void* stream) {
+    TwRequest tw{};
+    tw.tw_out = total_weight_out_dev;
+    tw.world = 1;
+    tw.rank = 0;
+    if (xchg && xchg->world > 1) {
+        tw.world = xchg->world;
+        tw.rank = xchg->rank;
+        for (int q = 0; q < xchg->world; ++q) {
+            CVCS_REQUIRE(xchg->peer[q], "cvcs_ce_fused_tw: the exchange block of rank %d is not mapped (cvcs_xchg_open_peer)", q);
+            tw.peer[q] = xchg->peer[q];
+        }
+    }
+    return ce_fused_launch(logits_dev, logits_dtype, layout, target_dev, target_dtype, weight_dev, ignore_index, B, C, H,
+                           W, 0.0, nullptr, dlogits_dev, argmax_dev, argmax_dtype, confmat_dev, loss_sums_dev, loss_out_dev,
+                           workspace_dev, static_cast<cudaStream_t>(stream), nullptr, 0, &tw);
 }
 
 int cvcs_eval_fused(const void* logits_dev, int logits_dtype, int layout, const void* target_dev, int target_dtype,

@@ -32,6 +32,19 @@ struct CeParams {
     int conf_reps;   // generic kernel: shared-memory replicas of the C*C bins (0 = global atomics)
     unsigned long long* status;  // nullable: += #out-of-bounds labels (metrics mode, cvcs_eval_fused)
     int no_loss;     // 1: metrics mode — argmax + confusion matrix only, no softmax / loss (loss_sums may be NULL)
+    // total weight computed by the kernel itself (TMA variant): a label pre-pass by every CTA, a grid-wide barrier
+    // and — across GPUs — a one-shot exchange over peer-mapped memory, all before the first gradient is written
+    int tw_mode;                 // 0: inv_tw / inv_tw_dev above; 1: in-kernel pre-pass
+    double* tw_out;              // nullable f64[2]: {Σ v·w[y] (global), 1/Σ}
+    int xworld, xrank;           // ranks taking part in the exchange (1 = this GPU only)
+    XchgBlock* xpeer[kXMaxRanks];  // every rank's exchange block (xpeer[xrank] is the local one)
+};
+
+// what cvcs_ce_fused_tw asks of the launcher: compute the total weight in the kernel, optionally exchanged across ranks
+struct TwRequest {
+    double* tw_out;                // nullable f64[2]
+    int world, rank;
+    XchgBlock* peer[kXMaxRanks];   // peer[rank] = local block; unused when world == 1
 };
 
 // launchers (one translation unit each)
@@ -113,6 +126,20 @@ __device__ __forceinline__ void store_argmax(const CeParams& p, long long pix, c
     }
 }
 
+// Four u8 labels of one 32-bit word classified at once (C <= 128).  Results carry one flag per byte in bit 7:
+//   inval7: the label is not a valid class (>= C, or equal to ignore_index)
+//   bad7  : the label is out of bounds (>= C and not ignore_index)
+// ge_add = (128 - C) * 0x01010101; ign4 = the ignore byte replicated (0 if ignore_index is not a byte value) and
+// ne_or = 0x80808080 in that case (no label can match), else 0.
+__device__ __forceinline__ void classify_labels_u8x4(uint32_t w, uint32_t ge_add, uint32_t ign4, uint32_t ne_or,
+                                                     uint32_t& inval7, uint32_t& bad7) {
+    const uint32_t ge = ((w & 0x7f7f7f7fu) + ge_add) | w;                       // bit 7: byte >= C
+    const uint32_t z = w ^ ign4;
+    const uint32_t ne = (((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z) | ne_or;        // bit 7: byte != ignore
+    bad7 = ge & ne & 0x80808080u;
+    inval7 = (ge | ~ne) & 0x80808080u;
+}
+
 // ---- per-pixel arithmetic ------------------------------------------------------------------------
 // MUFU approximations without the range-fixing prologue/epilogue the libdevice wrappers add: the
 // arguments are range limited by construction (ex2: x - max <= 0, underflow to 0 is the right
@@ -133,7 +160,11 @@ __device__ __forceinline__ float rcp_ftz(float x) {
     return y;
 }
 
-#ifdef CVCS_X_PACKED_ARGMAX
+// ---- packed bf16x2 helpers (bf16 logits, NCHW: a 32-bit word of a class plane is a pixel pair) ----------
+// HMNMX2.BF16 / HSET2.BF16 / HFMA2.BF16 work on both halves at once; sub.f32.bf16 (sm_100: FHADD.BF16 with an
+// .H0/.H1 operand selector) subtracts an fp32 from a bf16 half EXACTLY into fp32, so the packed words never have to
+// be unpacked.  max ignores NaN operands and returns +0 for {-0, +0}; set.eq is an IEEE compare (-0 == +0, NaN != NaN):
+// the same tie rules as the fp32 FMNMX / FSETP path.
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
     uint32_t d;
     asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
@@ -144,7 +175,76 @@ __device__ __forceinline__ uint32_t bf16x2_eq_mask(uint32_t a, uint32_t b) {
     asm("set.eq.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));   // 0xffff per half where equal
     return d;
 }
-#endif
+__device__ __forceinline__ uint32_t bf16x2_nan_mask(uint32_t a) {
+    uint32_t d;
+    asm("set.nan.u32.bf16x2 %0, %1, %1;" : "=r"(d) : "r"(a));         // 0xffff per half that is NaN
+    return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_add(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// (mask & a) | (~mask & b), one LOP3
+__device__ __forceinline__ uint32_t lop3_select(uint32_t a, uint32_t b, uint32_t mask) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(mask), "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned short bf16_half(uint32_t w, int hi) {
+    return static_cast<unsigned short>(hi ? (w >> 16) : (w & 0xffffu));
+}
+// bf16 - fp32 -> fp32, exact (mixed-precision add of PTX ISA 8.6, sm_100+)
+__device__ __forceinline__ float sub_f32_bf16(unsigned short a, float b) {
+    float d;
+    asm("sub.f32.bf16 %0, %1, %2;" : "=f"(d) : "h"(a), "f"(b));
+    return d;
+}
+
+// ---- one-shot exchange of the per-rank total weight over peer-mapped memory (NVLink) ---------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// One thread per CTA.  `writer` (one thread of the grid) publishes this rank's value to every rank's block; every caller
+// then waits for all ranks' values of this exchange in its OWN block and adds them in rank order.  A peer that never
+// arrives (or has overrun the ring) ends the wait after ~4 s with NaN and a count in errors — never a hang.
+__device__ __forceinline__ double xchg_total_weight(const CeParams& p, double mine, bool writer) {
+    XchgBlock* local = p.xpeer[p.xrank];
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&local->seq) + 1ull;
+    const int slot = static_cast<int>(seq % kXDepth);
+    const unsigned int tag = static_cast<unsigned int>(seq);
+    if (writer) {
+        for (int q = 0; q < p.xworld; ++q) *reinterpret_cast<volatile double*>(&p.xpeer[q]->slots[slot][p.xrank]) = mine;
+        __threadfence_system();
+        for (int q = 0; q < p.xworld; ++q) st_release_sys_u32(&p.xpeer[q]->flags[slot][p.xrank], tag);
+    }
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    double tot = 0.0;
+    for (int q = 0; q < p.xworld; ++q) {
+        while (ld_acquire_sys_u32(&local->flags[slot][q]) != tag) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) {
+                atomicAdd(&local->errors, 1ull);
+                return __longlong_as_double(0x7ff8000000000000ll);
+            }
+            __nanosleep(64);
+        }
+        tot += *reinterpret_cast<volatile double*>(&local->slots[slot][q]);
+    }
+    return tot;
+}
 
 // torch.max over one pixel's classes with its NaN rule, from a fetch functor (slow path only).
 template <int C, typename F>
@@ -221,11 +321,17 @@ __device__ __forceinline__ int pixel_ce(float (&x)[C], int tv, const float* __re
 }
 
 // Block-reduce {Σ w·nll, Σ w}; the last CTA folds the per-block fp64 partials in a fixed
-// order -> bit-stable run to run, no float atomics.  Must be called by all NWARPS*32 threads.
-template <int NWARPS>
+// order -> bit-stable run to run, no float atomics.  Must be called by threads 0..NWARPS*32-1: the whole CTA
+// (BAR = 0, __syncthreads) or the first NWARPS warps of a wider one, synchronised on named barrier BAR — the TMA-staged
+// kernel runs it on its consumer warps while the store warp is still draining the last gradients.
+template <int NWARPS, int BAR = 0>
 __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, double wsum, unsigned int bad) {
     __shared__ double red[2 * NWARPS];
     __shared__ unsigned int is_last;
+    const auto sync = [] {
+        if constexpr (BAR == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NWARPS * 32) : "memory");
+    };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     lsum = warp_sum(lsum);
     wsum = warp_sum(wsum);
@@ -235,7 +341,7 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
         red[NWARPS + warp] = wsum;
         if (bad) atomicAdd(&p.ws->bad, static_cast<unsigned long long>(bad));
     }
-    __syncthreads();
+    sync();
     if (threadIdx.x == 0) {
         double a = 0.0, b = 0.0;
 #pragma unroll
@@ -249,9 +355,10 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
         const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
         is_last = (t == gridDim.x - 1);
     }
-    __syncthreads();
+    sync();
     if (!is_last) return;
     __threadfence();
+    const unsigned long long nbad = __ldcg(&p.ws->bad);   // every CTA's count landed before its ticket
     double a = 0.0, b = 0.0;
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += NWARPS * 32) {
         a += __ldcg(&p.ws->partial[2 * i]);
@@ -259,12 +366,12 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
     }
     a = warp_sum(a);
     b = warp_sum(b);
-    __syncthreads();
+    sync();
     if (lane == 0) {
         red[warp] = a;
         red[NWARPS + warp] = b;
     }
-    __syncthreads();
+    sync();
     if (threadIdx.x == 0) {
         a = 0.0;
         b = 0.0;
@@ -273,7 +380,6 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
             a += red[w];
             b += red[NWARPS + w];
         }
-        const unsigned long long nbad = atomicAdd(&p.ws->bad, 0ull);
         if (p.status && nbad) atomicAdd(p.status, nbad);
         if (p.loss_sums) {
             p.loss_sums[0] = a;
@@ -288,6 +394,8 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
         p.ws->bad = 0ull;
         p.ws->ticket = 0u;
         p.ws->next_chunk = 0u;
+        p.ws->gbar = 0u;
+        if (p.tw_mode == 1 && p.xworld > 1) p.xpeer[p.xrank]->seq += 1ull;   // every CTA read it long ago (grid barrier)
         __threadfence();
     }
 }

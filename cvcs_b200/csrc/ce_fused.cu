@@ -14,11 +14,51 @@ namespace cvcs {
 int ce_tma_launch_f32(const CeParams& p, int layout, cudaStream_t stream, bool* handled);
 int ce_tma_launch_bf16(const CeParams& p, int layout, cudaStream_t stream, bool* handled);
 
+int label_hist_launch(const void*, int, long long, int, long long, unsigned long long*, const float*, double*, void*,
+                      cudaStream_t);
+
+// tw_mode 1 on a shape the TMA-staged kernel does not take (odd sizes, int64 labels, C > 21, a forced variant): the
+// same result from two launches — K4 (lean: Σ v·w[y] only) into tw_out, then K1 reading 1/Σ from there.  Single GPU
+// only: the cross-GPU exchange lives in the TMA kernel's prologue.
+static int tw_fallback(CeParams p, int logits_dtype, int layout, int target_dtype, cudaStream_t stream) {
+    if (p.xworld > 1)
+        return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_ce_fused_tw: the cross-GPU exchange needs a shape the TMA-staged kernel takes "
+                         "(u8 labels, 16-byte aligned tensors, H*W %% 16 == 0, 2 <= C <= %d)", kMaxRegC);
+    CVCS_REQUIRE(p.tw_out, "cvcs_ce_fused_tw: total_weight_out_dev is needed for this shape (two-launch fallback)");
+    int rc = label_hist_launch(p.target, target_dtype, p.n_pixels, p.C, p.ignore_index, nullptr, p.weight, p.tw_out, p.ws, stream);
+    if (rc) return rc;
+    p.tw_mode = 0;
+    p.inv_tw_dev = p.tw_out + 1;
+    const int forced = get_option(CVCS_OPT_CE_PATH);
+    const int esize = logits_dtype == CVCS_F32 ? 4 : 2;
+    (void)esize;
+    auto aligned = [](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
+    const bool ptr16 = aligned(p.logits, 16) && aligned(p.dlogits, 16) && aligned(p.target, 16) && aligned(p.argmax, 16);
+    bool handled = false;
+    if (forced != 3 && p.C >= 2 && p.C <= kMaxRegC && ptr16) {
+        const bool tma_ok = layout == CVCS_NCHW ? (p.hw % 16 == 0) : (p.n_pixels % 16 == 0);
+        if (tma_ok && forced != 2) {
+            rc = logits_dtype == CVCS_F32 ? ce_tma_launch_f32(p, layout, stream, &handled) : ce_tma_launch_bf16(p, layout, stream, &handled);
+            if (handled) return rc;
+        }
+        if (layout == CVCS_NCHW && forced != 1) {
+            const int vec = logits_dtype == CVCS_F32 ? 4 : (p.C <= 12 ? 8 : 4);
+            if (p.hw % vec == 0) {
+                p.n_items = p.n_pixels / vec;
+                p.items_per_image = static_cast<unsigned int>(p.hw / vec);
+                rc = ce_direct_launch(p, logits_dtype, vec, stream, &handled);
+                if (handled) return rc;
+            }
+        }
+    }
+    return ce_generic_launch(p, logits_dtype, layout, stream);
+}
+
 int ce_fused_launch(const void* logits, int logits_dtype, int layout, const void* target, int target_dtype,
                     const float* weight, long long ignore_index, int B, int C, int H, int W,
                     double inv_total_weight, const double* inv_total_weight_dev, void* dlogits, void* argmax,
                     int argmax_dtype, unsigned long long* confmat, double* loss_sums, float* loss_out,
-                    void* workspace, cudaStream_t stream, unsigned long long* status, int no_loss) {
+                    void* workspace, cudaStream_t stream, unsigned long long* status, int no_loss, const TwRequest* tw) {
     CVCS_REQUIRE(logits && target && (loss_sums || no_loss) && workspace, "cvcs_ce_fused: NULL logits/target/loss_sums/workspace");
     CVCS_REQUIRE(!(no_loss && dlogits), "cvcs_eval_fused: metrics mode has no gradients");
     CVCS_REQUIRE(logits_dtype == CVCS_F32 || logits_dtype == CVCS_BF16, "cvcs_ce_fused: logits dtype tag %d (want f32/bf16)", logits_dtype);
@@ -54,6 +94,19 @@ int ce_fused_launch(const void* logits, int logits_dtype, int layout, const void
     p.argmax_i64 = argmax_dtype == CVCS_I64;
     p.status = status;
     p.no_loss = no_loss;
+    p.xworld = 1;
+    if (tw && dlogits) {
+        // total weight computed by K1 itself (label pre-pass + grid barrier [+ exchange]); forward-only calls do not need it
+        CVCS_REQUIRE(tw->world >= 1 && tw->world <= kXMaxRanks && tw->rank >= 0 && tw->rank < tw->world,
+                     "cvcs_ce_fused_tw: bad exchange geometry (world %d, rank %d)", tw->world, tw->rank);
+        p.tw_mode = 1;
+        p.tw_out = tw->tw_out;
+        p.xworld = tw->world;
+        p.xrank = tw->rank;
+        for (int q = 0; q < tw->world; ++q) p.xpeer[q] = tw->peer[q];
+        p.inv_tw_dev = nullptr;
+        p.inv_tw = 0.0;
+    }
 
     const int forced = get_option(CVCS_OPT_CE_PATH);  // 0 auto, 1 tma, 2 direct, 3 generic
     const int esize = logits_dtype == CVCS_F32 ? 4 : 2;
@@ -62,13 +115,17 @@ int ce_fused_launch(const void* logits, int logits_dtype, int layout, const void
     bool handled = false;
     int rc = CVCS_OK;
 
+    if (p.tw_mode == 1 && !(forced != 3 && C >= 2 && C <= kMaxRegC && ptr16)) return tw_fallback(p, logits_dtype, layout, target_dtype, stream);
     if (forced != 3 && C >= 2 && C <= kMaxRegC && ptr16) {
         // ---- TMA-staged: every bulk copy must be a multiple of 16 bytes
         const bool tma_ok = layout == CVCS_NCHW ? (hw % 16 == 0) : (n_pixels % 16 == 0);
+        if (p.tw_mode == 1 && !(tma_ok && forced != 2 && forced != 3 && target_dtype == CVCS_U8))
+            return tw_fallback(p, logits_dtype, layout, target_dtype, stream);
         if (tma_ok && forced != 2) {
             rc = logits_dtype == CVCS_F32 ? ce_tma_launch_f32(p, layout, stream, &handled)
                                           : ce_tma_launch_bf16(p, layout, stream, &handled);
             if (handled) return rc;
+            if (p.tw_mode == 1) return tw_fallback(p, logits_dtype, layout, target_dtype, stream);
         }
         // ---- direct NCHW: f32 4 pixels/thread; bf16 8 pixels/thread up to C=12, else 4
         if (layout == CVCS_NCHW && forced != 1) {

@@ -169,9 +169,74 @@ __device__ __forceinline__ void sts_elem(unsigned char* base, int idx, float v) 
     else *reinterpret_cast<unsigned short*>(base + 2 * idx) = static_cast<unsigned short>(pack_bf16(v, 0.f) & 0xffffu);
 }
 
-template <typename T, int C, int VECP, bool NHWC, bool PRIV, bool GRAD, bool LOSS = true>
+// ---- Σ v·w[y] inside K1 (tw_mode 1) --------------------------------------------------------------------------------
+// nn.CrossEntropyLoss's 'mean' divides every gradient by the total weight of the WHOLE batch (utils.py:230,238), so it
+// must be known before the first gradient is written.  Instead of a separate K4 launch the 256 consumer threads of
+// every CTA first sum a 256-entry weight table over their slice of the byte labels (16.8 MB for cfg3: ~3 us, and the
+// labels are then L2-resident for the main loop), the grid meets at one barrier (all CTAs are resident: persistent
+// grid, cooperative launch), every CTA folds the per-CTA partials in the same fixed order, and with several GPUs one
+// thread publishes the sum to every peer over NVLink and every CTA adds the ranks' values in rank order.  The loader
+// warp is not involved: its first bulk loads are in flight meanwhile.  Called by threads 0..kThreads-1.
+template <int C>
+__device__ __forceinline__ double prepass_total_weight(const CeParams& p, int tid) {
+    __shared__ float wlut[256];
+    __shared__ double red[kWarps];
+    __shared__ double total;
+    const auto csync = [] { asm volatile("bar.sync %0, %1;" ::"n"(kConsumerBar), "n"(kThreads) : "memory"); };
+    wlut[tid] = (tid < C && static_cast<long long>(tid) != p.ignore_index) ? (p.weight ? p.weight[tid] : 1.0f) : 0.f;
+    csync();
+    const uint8_t* __restrict__ tgt = reinterpret_cast<const uint8_t*>(p.target);
+    const long long n16 = p.n_pixels / 16;
+    const long long per = (n16 + gridDim.x - 1) / gridDim.x;
+    const long long lo = static_cast<long long>(blockIdx.x) * per;
+    const long long hi = lo + per < n16 ? lo + per : n16;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long i = lo + tid; i < hi; i += kThreads) {
+        const uint4 v = *reinterpret_cast<const uint4*>(tgt + 16 * i);     // default caching: stays in L2 for the main loop
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k & 3] += wlut[(w4[k / 4] >> (8 * (k % 4))) & 0xff];
+    }
+    if (blockIdx.x == 0) {
+        const long long i = n16 * 16 + tid;
+        if (i < p.n_pixels) a[0] += wlut[tgt[i]];
+    }
+    double s = warp_sum(static_cast<double>((a[0] + a[1]) + (a[2] + a[3])));
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    csync();
+    if (tid == 0) {
+        double b = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) b += red[w];
+        p.ws->pre[blockIdx.x] = b;
+        __threadfence();
+        atomicAdd(&p.ws->gbar, 1u);
+        while (ld_acquire_gpu_u32(&p.ws->gbar) < gridDim.x) __nanosleep(32);
+    }
+    csync();
+    if (tid < 32) {
+        double v = 0.0;
+        for (unsigned int i = tid; i < gridDim.x; i += 32) v += __ldcg(&p.ws->pre[i]);   // same order in every CTA
+        v = warp_sum(v);
+        if (tid == 0) {
+            if (p.xworld > 1) v = xchg_total_weight(p, v, blockIdx.x == 0);
+            total = v;
+            if (blockIdx.x == 0 && p.tw_out) {
+                p.tw_out[0] = v;
+                p.tw_out[1] = 1.0 / v;
+            }
+        }
+    }
+    csync();
+    return total;
+}
+
+// SUB: sub-chunks of kThreads*VECP pixels per stage.  A consumer thread handles VECP consecutive pixels of every
+// sub-chunk, so SUB > 1 doubles the bytes per bulk copy and halves the per-stage bookkeeping per pixel without
+// widening the thread's register working set.
+template <typename T, int C, int VECP, bool NHWC, bool PRIV, bool GRAD, bool LOSS = true, int SUB = 1>
 __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CeParams p, const Geom g) {
-    constexpr int P = kThreads * VECP;
+    constexpr int P = kThreads * VECP * SUB;
     constexpr int ES = sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ float wsm[C];
@@ -180,7 +245,9 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
 
     const int tid = threadIdx.x;
 #ifdef CVCS_X_TIMING
-    unsigned long long t_start = 0;
+    // experiment build: globaltimer stamps of CTAs 0..255 in ws->hist (start / first stage ready / last chunk done /
+    // before the loss epilogue), the very end of the grid in hist[1024]; the caller re-zeroes the workspace
+    unsigned long long t_start = 0, t_first = 0, t_loop = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 #endif
     constexpr bool do_grad = GRAD;
@@ -200,8 +267,14 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
-    if (tid < C) wsm[tid] = p.weight ? p.weight[tid] : 1.0f;
-    __syncthreads();
+    // Programmatic dependent launch: the next kernel in the stream (e.g. the following K1) may become resident
+    // as this grid's CTAs exit and run ITS prologue; everything above touches only shared memory, everything
+    // below may read what the predecessor wrote (logits, 1/Σw from K4, the workspace counters) and waits for it.
+    // Both are no-ops when the launch carries no programmatic-serialization attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __syncthreads();                                  // barriers initialised
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // the loader goes straight to its first bulk loads; the consumers fetch the class weights and 1/Σw meanwhile
 
     const long long n_chunks = p.n_items;
 
@@ -285,27 +358,49 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                 pending = ring.s;
                 ring.next(S);
             }
-            bulk_wait_all();
+            bulk_wait_read<0>();   // the last stores have left shared memory: the CTA may exit (the grid's end makes them visible)
+#ifdef CVCS_X_TIMING
+            unsigned long long t_st;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_st));
+            atomicMax(&p.ws->hist[1025], t_st);
+#endif
         }
     } else {
         // ================= consumers =================
+        if (tid < C) wsm[tid] = p.weight ? p.weight[tid] : 1.0f;
+        float inv_tw = do_grad ? static_cast<float>(p.inv_tw_dev ? __ldcg(p.inv_tw_dev) : p.inv_tw) : 0.f;
+        if constexpr (do_grad) {
+            if (p.tw_mode == 1) inv_tw = static_cast<float>(1.0 / prepass_total_weight<C>(p, tid));   // grid-wide; see below
+        }
         BinAcc<PRIV, kConsumerBar> conf;
         if (do_conf) conf.init(smem + g.hist_off, C * C);
-        const float inv_tw = do_grad ? static_cast<float>(p.inv_tw_dev ? *p.inv_tw_dev : p.inv_tw) : 0.f;
+        else BinAcc<PRIV, kConsumerBar>::sync();      // wsm visible to all consumers
         const int ign8 = ignore_as_int_u8(p.ignore_index);
+        // byte-parallel label classification constants (u8 labels, C <= 128): see classify_labels_u8x4
+        const uint32_t lab_ge_add = static_cast<uint32_t>(128 - C) * 0x01010101u;
+        const uint32_t lab_ign4 = static_cast<uint32_t>(ign8 >= 0 ? ign8 : 0) * 0x01010101u;
+        const uint32_t lab_ne_or = ign8 >= 0 ? 0u : 0x80808080u;   // no u8 label can equal an ignore_index outside [0, 255]
         unsigned int since_flush = 0;
-        Ring ring{0, 0u};
-        const int pix_t0 = tid * VECP;  // this thread's first pixel inside a chunk
+        // ring position held as addresses (advanced by addition, no per-stage multiplies)
+        int rs = 0;
+        uint32_t rphase = 0u;
+        uint32_t full_bar = bar0;
+        unsigned char* stage = smem + g.stage_off;
+        const Chunk* dsc = desc;
 
         for (;;) {
-            unsigned char* stage = smem + g.stage_off + ring.s * g.stage_bytes;
-            if (g.wait_hint) mbar_wait<true>(bar0 + 8 * ring.s, ring.phase);
-            else mbar_wait<false>(bar0 + 8 * ring.s, ring.phase);
-            const Chunk ck = desc[ring.s];
+            mbar_wait<true>(full_bar, rphase);   // suspends in hardware (the option only affects the producers)
+#ifdef CVCS_X_TIMING
+            if (tid == 0 && t_first == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
+#endif
+            const Chunk ck = *dsc;
             if (ck.n < 0) {                   // sentinel: pass it on to the storer and leave
-                mbar_arrive(bar0 + 8 * (kMaxStages + ring.s));
+                mbar_arrive(full_bar + 8 * kMaxStages);
                 break;
             }
+#pragma unroll 1
+            for (int sub = 0; sub < SUB; ++sub) {
+            const int pix_t0 = sub * (kThreads * VECP) + tid * VECP;  // this thread's first pixel of the sub-chunk
             if (pix_t0 < ck.n) {
                 // element index of (class c, pixel j of the chunk) inside the stage
                 auto eidx = [&](int c, int j) { return NHWC ? j * C + c : c * P + j; };
@@ -343,92 +438,140 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                     if constexpr (ES == 4) return __uint_as_float(raw[e]);
                     else return (e & 1) ? bf16_hi(raw[e >> 1]) : bf16_lo(raw[e >> 1]);
                 };
-                // ---- labels
-                int t[VECP];
+                // ---- labels -> per pixel: the class clamped into [0, C) (what the target-logit gather uses), a
+                // valid flag (in range and not ignore_index) and the count of out-of-bounds labels
+                int tcl[VECP];
+                bool valid[VECP];
                 const unsigned char* lab = stage + g.label_off;
                 if (p.target_i64) {
 #pragma unroll
                     for (int k = 0; k < VECP; ++k) {
                         const uint2 v = *reinterpret_cast<const uint2*>(lab + (static_cast<size_t>(pix_t0) + k) * 8);
-                        t[k] = decode_label_i64(v.x, v.y, p.ignore_index);
+                        const int tv = decode_label_i64(v.x, v.y, p.ignore_index);
+                        valid[k] = static_cast<unsigned int>(tv) < static_cast<unsigned int>(C);
+                        tcl[k] = valid[k] ? tv : 0;
+                        bad += (!valid[k] && tv != -1) ? 1u : 0u;
+                    }
+                } else if constexpr (VECP % 4 == 0 && C <= 128) {
+                    // four labels per 32-bit word, classified byte-parallel: two flag words (bit 7 of each byte) give
+                    // "not a valid class" and "out of bounds"; one predicate per pixel and one test per word remain
+#pragma unroll
+                    for (int j = 0; j < VECP / 4; ++j) {
+                        const uint32_t w = *reinterpret_cast<const uint32_t*>(lab + pix_t0 + 4 * j);
+                        uint32_t inval7, bad7;
+                        classify_labels_u8x4(w, lab_ge_add, lab_ign4, lab_ne_or, inval7, bad7);
+                        if (bad7) bad += static_cast<unsigned int>(__popc(bad7));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            valid[4 * j + k] = (inval7 & (0x80u << (8 * k))) == 0u;
+                            tcl[4 * j + k] = min(static_cast<int>((w >> (8 * k)) & 0xffu), C - 1);
+                        }
                     }
                 } else {
-                    uint32_t w[VECP >= 4 ? VECP / 4 : 1];
-                    if constexpr (VECP == 8) {
-                        const uint2 v = *reinterpret_cast<const uint2*>(lab + pix_t0);
-                        w[0] = v.x; w[1] = v.y;
-                    } else if constexpr (VECP == 4) {
-                        w[0] = *reinterpret_cast<const uint32_t*>(lab + pix_t0);
-                    } else if constexpr (VECP == 2) {
-                        w[0] = *reinterpret_cast<const unsigned short*>(lab + pix_t0);
-                    } else {
-                        w[0] = lab[pix_t0];
-                    }
+                    uint32_t w = 0;
+                    if constexpr (VECP == 2) w = *reinterpret_cast<const unsigned short*>(lab + pix_t0);
+                    else w = lab[pix_t0];
+                    static_assert(VECP <= 2 || (VECP % 4 == 0 && C <= 128), "label decode");
 #pragma unroll
                     for (int k = 0; k < VECP; ++k) {
-                        const int v = (w[k / 4] >> (8 * (k % 4))) & 0xff;
-                        t[k] = (v == ign8) ? -1 : v;
+                        const int v = (w >> (8 * k)) & 0xff;
+                        const bool in_range = v < C;
+                        valid[k] = in_range && v != ign8;
+                        tcl[k] = min(v, C - 1);
+                        bad += (!in_range && v != ign8) ? 1u : 0u;
                     }
                 }
                 // ---- math.  fp32: one pixel at a time; bf16 NCHW: two pixels at a time, because a 32-bit
                 // word of a class plane holds the pixel pair (2j, 2j+1) and both gradients are packed with one
                 // cvt.rn.bf16x2 (the compiler interleaves the unrolled groups either way)
                 constexpr int PP = (ES == 2 && VECP % 2 == 0) ? 2 : 1;
+                constexpr bool kPackedPair = ES == 2 && PP == 2 && !NHWC;
+                // byte address of (class c, thread-local pixel k) inside the stage: one multiply-add on the
+                // thread's base (the target logit is gathered, and its gradient patched, by dynamic class index)
+                constexpr int kClassStride = NHWC ? ES : P * ES;
+                constexpr int kPixStride = NHWC ? C * ES : ES;
+                unsigned char* const px0 = stage + static_cast<size_t>(pix_t0) * kPixStride;
+                auto tptr = [&](int cls, int k) { return px0 + cls * kClassStride + k * kPixStride; };
                 int amax[VECP];
                 float gfix[VECP];     // gradient of the target class, patched into the stage afterwards
                 float step_l = 0.f, step_w = 0.f;
                 bool anomalous = false;  // some pixel's Σexp is NaN (NaN / +inf / all -inf logits)
 #pragma unroll
                 for (int k0 = 0; k0 < VECP; k0 += PP) {
+                    if constexpr (kPackedPair) {
+                        // ---- bf16 NCHW, a pixel pair per 32-bit word: everything that does not need fp32 stays on
+                        // the packed words.  max = HMNMX2.BF16, first-max index = HSET2.EQ mask + one LOP3 per class
+                        // (both pixels at once), and x - max goes straight from the packed half into fp32 with the
+                        // mixed-precision add (sub.f32.bf16 -> FHADD.BF16, exact) — no unpack instructions at all.
+                        uint32_t wq[C];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) wq[c] = raw[ridx(c, k0) >> 1];
+                        uint32_t m2 = wq[0];
+#pragma unroll
+                        for (int c = 1; c < C; ++c) m2 = bf16x2_max(m2, wq[c]);
+                        uint32_t arg2 = static_cast<uint32_t>(C - 1) * 0x00010001u;
+#pragma unroll
+                        for (int c = C - 2; c >= 0; --c)
+                            arg2 = lop3_select(static_cast<uint32_t>(c) * 0x00010001u, arg2, bf16x2_eq_mask(wq[c], m2));
+                        amax[k0] = static_cast<int>(arg2 & 0xffffu);
+                        amax[k0 + 1] = static_cast<int>(arg2 >> 16);
+                        if constexpr (!LOSS) {
+                            // metrics mode: a NaN anywhere in the row (or +inf with -inf) makes the packed sum NaN
+                            uint32_t s2 = wq[0];
+#pragma unroll
+                            for (int c = 1; c < C; ++c) s2 = bf16x2_add(s2, wq[c]);
+                            anomalous |= bf16x2_nan_mask(s2) != 0u;
+                        } else {
+                            float e[2][C], r[2] = {0.f, 0.f};
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const int k = k0 + q;
+                                const unsigned short xtb = *reinterpret_cast<const unsigned short*>(tptr(tcl[k], k));
+                                const float wc = wsm[tcl[k]];
+                                const float w = valid[k] ? wc : 0.f;
+                                const float m = q ? bf16_hi(m2) : bf16_lo(m2);
+                                float s = 0.f;
+#pragma unroll
+                                for (int c = 0; c < C; ++c) {
+                                    e[q][c] = ex2_ftz(sub_f32_bf16(bf16_half(wq[c], q), m) * kLog2e);
+                                    s = c ? s + e[q][c] : e[q][c];
+                                }
+                                anomalous |= (s != s);
+                                const float dt = sub_f32_bf16(xtb, m);            // x_t - max <= 0, exact
+                                const float nll = fmaf(lg2_ftz(s), kLn2, -dt);
+                                step_l += valid[k] ? w * nll : 0.f;
+                                step_w += w;
+                                if constexpr (do_grad) {
+                                    const float gsc = valid[k] ? w * inv_tw : 0.f;  // exact zeros at ignored pixels
+                                    r[q] = gsc * rcp_ftz(s);
+                                    gfix[k] = fmaf(ex2_ftz(dt * kLog2e), r[q], -gsc);
+                                }
+                            }
+                            if constexpr (do_grad) {
+#pragma unroll
+                                for (int c = 0; c < C; ++c) raw[ridx(c, k0) >> 1] = pack_bf16(e[0][c] * r[0], e[1][c] * r[1]);
+                            }
+                        }
+                        continue;
+                    }
                     float x[PP][C];
                     float r[PP];
-#ifdef CVCS_X_PACKED_ARGMAX
-                    // experiment: max and first-max index of the pixel pair on the packed bf16 words (max.bf16x2 +
-                    // set.eq.bf16x2 masks + one LOP3 per class) instead of per pixel in fp32
-                    [[maybe_unused]] uint32_t m2 = 0u, arg2 = 0u;
-                    if constexpr (ES == 2 && PP == 2 && !NHWC && LOSS) {
-                        m2 = raw[ridx(0, k0) >> 1];
-#pragma unroll
-                        for (int c = 1; c < C; ++c) m2 = bf16x2_max(m2, raw[ridx(c, k0) >> 1]);
-                        arg2 = static_cast<uint32_t>(C - 1) * 0x00010001u;
-#pragma unroll
-                        for (int c = C - 2; c >= 0; --c) {
-                            const uint32_t hit = bf16x2_eq_mask(raw[ridx(c, k0) >> 1], m2);
-                            arg2 = arg2 ^ ((arg2 ^ (static_cast<uint32_t>(c) * 0x00010001u)) & hit);
-                        }
-                    }
-#endif
 #pragma unroll
                     for (int q = 0; q < PP; ++q) {
                         const int k = k0 + q;
-                        const int tv = t[k];
-                        const bool valid = static_cast<unsigned int>(tv) < static_cast<unsigned int>(C);
-                        bad += (!valid && tv != -1) ? 1u : 0u;
-                        const int tc = valid ? tv : 0;
                         // the target logit and its class weight by dynamic index from shared memory
                         float xt = 0.f, w = 0.f;
                         if constexpr (LOSS) {
-                            xt = lds_elem<T>(stage, eidx(tc, pix_t0 + k));
-                            w = valid ? wsm[tc] : 0.f;
+                            if constexpr (ES == 4) xt = *reinterpret_cast<const float*>(tptr(tcl[k], k));
+                            else xt = __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(tptr(tcl[k], k))) << 16);
+                            w = wsm[tcl[k]];
+                            w = valid[k] ? w : 0.f;
                         }
 #pragma unroll
                         for (int c = 0; c < C; ++c) x[q][c] = raw_get(ridx(c, k));
                         float m, s;
                         int arg;
                         if constexpr (LOSS) {
-#ifdef CVCS_X_PACKED_ARGMAX
-                            if constexpr (ES == 2 && PP == 2 && !NHWC) {
-                                m = q ? bf16_hi(m2) : bf16_lo(m2);
-                                arg = static_cast<int>(q ? (arg2 >> 16) : (arg2 & 0xffffu));
-                                x[q][0] = exp_shifted<true>(x[q][0], m);
-                                s = x[q][0];
-#pragma unroll
-                                for (int c = 1; c < C; ++c) {
-                                    x[q][c] = exp_shifted<true>(x[q][c], m);
-                                    s += x[q][c];
-                                }
-                            } else
-#endif
                             softmax_core<C, ES == 2>(x[q], m, s, arg);
                         } else {
                             // metrics mode: only the argmax is wanted.  Σ x is NaN exactly when the row holds a NaN
@@ -448,12 +591,12 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                         amax[k] = arg;
                         if constexpr (LOSS) {
                             const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
-                            step_l += valid ? w * nll : 0.f;
+                            step_l += valid[k] ? w * nll : 0.f;
                             step_w += w;
                         }
                         r[q] = 0.f;
                         if constexpr (do_grad) {
-                            const float gsc = valid ? w * inv_tw : 0.f;  // exact zeros at ignored pixels
+                            const float gsc = valid[k] ? w * inv_tw : 0.f;  // exact zeros at ignored pixels
                             r[q] = gsc * rcp_ftz(s);
                             gfix[k] = fmaf(exp_shifted<ES == 2>(xt, m), r[q], -gsc);
                         }
@@ -463,8 +606,6 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                         for (int c = 0; c < C; ++c) {
                             if constexpr (ES == 4) {
                                 raw[ridx(c, k0)] = __float_as_uint(x[0][c] * r[0]);
-                            } else if constexpr (PP == 2 && !NHWC) {
-                                raw[ridx(c, k0) >> 1] = pack_bf16(x[0][c] * r[0], x[PP - 1][c] * r[PP - 1]);
                             } else if constexpr (PP == 2 && NHWC) {
                                 // the pixel pair's 2C values are C consecutive words: word c holds flat elements 2c, 2c+1
                                 auto flat = [&](int e) { return e < C ? x[0][e < C ? e : 0] * r[0] : x[PP - 1][e < C ? 0 : e - C] * r[PP - 1]; };
@@ -487,9 +628,27 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                         amax[k] = argmax_nan_aware<C>([&](int c) { return lds_elem<T>(stage, eidx(c, pix_t0 + k)); });
                 }
                 if (do_conf) {
+                    if constexpr (PRIV) {
 #pragma unroll
-                    for (int k = 0; k < VECP; ++k)
-                        if (static_cast<unsigned int>(t[k]) < static_cast<unsigned int>(C)) conf.add(t[k] * C + amax[k]);
+                        for (int k = 0; k < VECP; ++k)
+                            if (valid[k]) conf.add(tcl[k] * C + amax[k]);
+                    } else {
+                        // shared bins (C*C > 64): equal (target, prediction) pairs of the thread's consecutive pixels are
+                        // merged first (masks and predictions have runs), then equal pairs across the warp
+                        int key[VECP];
+#pragma unroll
+                        for (int k = 0; k < VECP; ++k) key[k] = valid[k] ? tcl[k] * C + amax[k] : -1;
+                        unsigned int run = 0;
+#pragma unroll
+                        for (int k = 0; k < VECP; ++k) {
+                            ++run;
+                            const bool last = (k == VECP - 1) || key[k + 1 < VECP ? k + 1 : k] != key[k];
+                            if (last) {
+                                if (key[k] >= 0) conf.add_agg(key[k], run);
+                                run = 0;
+                            }
+                        }
+                    }
                 }
                 // ---- registers -> shared (in place), then the target-class entries
                 if constexpr (do_grad) {
@@ -507,41 +666,63 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                         }
                     }
 #pragma unroll
-                    for (int k = 0; k < VECP; ++k)
-                        if (static_cast<unsigned int>(t[k]) < static_cast<unsigned int>(C)) sts_elem<T>(stage, eidx(t[k], pix_t0 + k), gfix[k]);
+                    for (int k = 0; k < VECP; ++k) {
+                        if (valid[k]) {
+                            if constexpr (ES == 4) *reinterpret_cast<float*>(tptr(tcl[k], k)) = gfix[k];
+                            else *reinterpret_cast<unsigned short*>(tptr(tcl[k], k)) = static_cast<unsigned short>(pack_bf16(gfix[k], 0.f) & 0xffffu);
+                        }
+                    }
                 }
                 if (do_arg) store_argmax<VECP>(p, ck.pix0 + pix_t0, amax);
             }
+            if (PRIV && do_conf) since_flush += VECP;
+            }   // sub-chunks
             if constexpr (do_grad) fence_async_smem();  // make the in-place gradients visible to the bulk store
-            mbar_arrive(bar0 + 8 * (kMaxStages + ring.s));
+            mbar_arrive(full_bar + 8 * kMaxStages);
             if (PRIV && do_conf) {
-                since_flush += VECP;
-                if (since_flush > 65535u - VECP) {
+                if (since_flush > 65535u - VECP * SUB) {
                     conf.flush(p.confmat);
                     since_flush = 0;
                 }
             }
-            ring.next(S);
+            ++dsc;
+            full_bar += 8;
+            stage += g.stage_bytes;
+            if (++rs == S) {
+                rs = 0;
+                rphase ^= 1u;
+                dsc = desc;
+                full_bar = bar0;
+                stage = smem + g.stage_off;
+            }
         }
-        if (do_conf) conf.flush(p.confmat);
-    }
 #ifdef CVCS_X_TIMING
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long t_end;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-        p.ws->hist[blockIdx.x] = t_end;          // experiment build only: the caller re-zeroes the workspace
-        p.ws->hist[512 + blockIdx.x] = t_start;
-    }
+        if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_loop));
 #endif
-    finish_loss<kBlock / 32>(p, lsum, wsum, bad);
+        if (do_conf) conf.flush(p.confmat);
+        // the loss epilogue runs on the consumer warps alone: it overlaps the store warp's last bulk stores
+        finish_loss<kWarps, kConsumerBar>(p, lsum, wsum, bad);
+#ifdef CVCS_X_TIMING
+        if (tid == 0) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            if (blockIdx.x < 256) {
+                p.ws->hist[blockIdx.x] = t_start;
+                p.ws->hist[256 + blockIdx.x] = t_first;
+                p.ws->hist[512 + blockIdx.x] = t_loop;
+                p.ws->hist[768 + blockIdx.x] = t_end;
+            }
+            atomicMax(&p.ws->hist[1024], t_end);
+        }
+#endif
+    }
 }
 
 // ---- launch ------------------------------------------------------------------------------------
-template <typename T, int C, int VECP, bool NHWC>
+template <typename T, int C, int VECP, bool NHWC, int SUB = 1>
 int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     constexpr bool PRIV = C * C <= kPrivBinsMax;
-    constexpr int P = kThreads * VECP;
+    constexpr int P = kThreads * VECP * SUB;
     constexpr int ES = sizeof(T);
     CeParams p = p0;
     const int tsize = p.target_i64 ? 8 : 1;
@@ -558,16 +739,29 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     // (read stream only, issue-bound) wants warps and bytes in flight: 3 CTAs when 3 stages each still
     // fit (C=20: 0.58 -> 0.72 of peak), else 2 CTAs with as many stages as the budget allows.
     const bool grad = p.dlogits != nullptr;
-    int target_ctas = get_option(CVCS_OPT_TMA_CTAS);
-    if (target_ctas < 1 || target_ctas > 4) {
-        if (grad) target_ctas = (2 * 3 * g.stage_bytes > 128 * 1024) ? 1 : 2;
-        else target_ctas = ((233472 / 3 - 2048 - g.stage_off) / g.stage_bytes >= 3) ? 3 : 2;  // forward-only kernels fit 3 CTAs (64 regs)
+    auto kernel = p.dlogits ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, true, true, SUB>
+                            : (p.no_loss ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, false, false, SUB> : ce_tma_kernel<T, C, VECP, NHWC, PRIV, false, true, SUB>);
+    // static shared memory of the chosen kernel (barriers, descriptors, weight tables, reduction scratch): it counts
+    // against the SM's 228 KB like the dynamic part does
+    static thread_local int static_smem[3] = {-1, -1, -1};
+    const int kslot = p.dlogits ? 0 : (p.no_loss ? 1 : 2);
+    if (static_smem[kslot] < 0) {
+        cudaFuncAttributes fa;
+        CVCS_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
+        static_smem[kslot] = static_cast<int>(fa.sharedSizeBytes);
     }
-    const int per_cta = 233472 / target_ctas - 1024 - 1024;  // 228 KB per SM, 1 KB reserved per CTA, static smem
+    const int reserve = 1024 + ((static_smem[kslot] + 255) / 256) * 256;   // 1 KB per CTA taken by the system + static
+    int target_ctas = get_option(CVCS_OPT_TMA_CTAS);
+    const bool ctas_forced = target_ctas >= 1 && target_ctas <= 4;
+    if (!ctas_forced) {
+        if (grad) target_ctas = (2 * 3 * g.stage_bytes > 128 * 1024) ? 1 : 2;
+        else target_ctas = ((233472 / 3 - reserve - g.stage_off) / g.stage_bytes >= 3) ? 3 : 2;  // forward-only kernels fit 3 CTAs (64 regs)
+    }
+    const int per_cta = 233472 / target_ctas - reserve;  // 228 KB per SM
     int stages = (per_cta - g.stage_off) / g.stage_bytes;
-    if (stages < 3 && target_ctas > 1) {  // wide stages (i64 labels, large C): the whole SM
+    if ((stages < 3 && target_ctas > 1 && !ctas_forced) || stages < 2) {  // wide stages (i64 labels, large C): the whole SM
         target_ctas = 1;
-        stages = (226 * 1024 - g.stage_off) / g.stage_bytes;
+        stages = (227 * 1024 - reserve + 1024 - g.stage_off) / g.stage_bytes;
     }
     if (grad && stages > 3) stages = 3;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -582,10 +776,8 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     int smem = g.stage_off + stages * g.stage_bytes;
     // keep exactly `target_ctas` CTAs resident: the dynamic request is padded past what target + 1 could share
     // (more bytes in flight per SM than ~120 KB measurably lowers the sustained HBM rate)
-    const int min_smem = 233472 / (target_ctas + 1) - 1024 + 16;
+    const int min_smem = 233472 / (target_ctas + 1) - 1024 - static_smem[kslot] + 16;
     if (smem < min_smem) smem = min_smem;
-    auto kernel = p.dlogits ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, true>
-                            : (p.no_loss ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, false, false> : ce_tma_kernel<T, C, VECP, NHWC, PRIV, false, true>);
     int grid = 0;
     int rc = persistent_grid(kernel, kBlock, smem, &grid);
     if (rc) return rc;
@@ -602,8 +794,38 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
         if (reserve > 0 && reserve <= 32 && reserve < sms) grid -= (grid / sms) * reserve;
     }
     if (p.n_items < grid) grid = static_cast<int>(p.n_items < 1 ? 1 : p.n_items);
-    kernel<<<grid, kBlock, smem, stream>>>(p, g);
-    CVCS_CUDA_OK(cudaGetLastError());
+    if (p.tw_mode == 1) {
+        // the pre-pass meets at a grid-wide barrier: every CTA must be resident -> cooperative launch (the grid is the
+        // persistent one, sized from the occupancy query, so the launch is refused rather than deadlocked if it is not)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kBlock);
+        cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CVCS_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p, g));
+    } else if (get_option(CVCS_OPT_PDL) == 1) {
+        // programmatic stream serialization: this launch may start while the previous kernel of the stream drains
+        // (the kernel itself waits, griddepcontrol.wait, before it reads anything the predecessor wrote)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kBlock);
+        cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CVCS_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p, g));
+    } else {
+        kernel<<<grid, kBlock, smem, stream>>>(p, g);
+        CVCS_CUDA_OK(cudaGetLastError());
+    }
     return CVCS_OK;
 }
 
@@ -613,7 +835,7 @@ constexpr bool span_ok() {
     return !NHWC || (VECP * C * static_cast<int>(sizeof(T))) % 16 == 0;
 }
 
-template <typename T, int VECP, bool NHWC, int CLO, int CHI, int CC = CLO>
+template <typename T, int VECP, bool NHWC, int CLO, int CHI, int SUB = 1, int CC = CLO>
 int dispatch(const CeParams& p, cudaStream_t stream, bool* handled) {
     if constexpr (CC > CHI) {
         *handled = false;
@@ -622,10 +844,10 @@ int dispatch(const CeParams& p, cudaStream_t stream, bool* handled) {
         if constexpr (span_ok<T, CC, VECP, NHWC>()) {
             if (p.C == CC) {
                 *handled = true;
-                return launch<T, CC, VECP, NHWC>(p, stream, handled);
+                return launch<T, CC, VECP, NHWC, SUB>(p, stream, handled);
             }
         }
-        return dispatch<T, VECP, NHWC, CLO, CHI, CC + 1>(p, stream, handled);
+        return dispatch<T, VECP, NHWC, CLO, CHI, SUB, CC + 1>(p, stream, handled);
     }
 }
 

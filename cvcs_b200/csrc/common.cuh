@@ -36,9 +36,12 @@ struct Workspace {
     unsigned int ticket;          // last-block election counter
     unsigned int next_chunk;      // K1 (TMA variant): dynamic chunk claim counter
     unsigned long long bad;       // out-of-bounds label counter
-    unsigned long long pad1[6];
+    unsigned int gbar;            // K1 with its own label pre-pass: grid-wide arrival counter (zero on exit)
+    unsigned int pad0;
+    unsigned long long pad1[5];
     double partial[2 * kMaxGrid]; // per-block {Σ w·nll, Σ w}
     unsigned long long hist[kMaxHistBins];  // per-call label histogram (K4 / K5), zero on exit
+    double pre[kMaxGrid];         // K1 pre-pass: per-block Σ v·w[y] (overwritten by every launch that uses it)
 };
 constexpr size_t kWorkspaceBytes = 128 * 1024;
 static_assert(sizeof(Workspace) <= kWorkspaceBytes, "workspace too small");
@@ -54,6 +57,20 @@ inline int shared_bin_replicas(int nbins, int budget_bytes = 64 * 1024, int hard
     if (static_cast<long long>(nbins) * r * 4 > hard_limit_bytes) return 0;
     return r;
 }
+
+// ---- Σw exchange block (one per rank, in device memory mapped into every peer: CUDA IPC over NVLink) ---------------
+// Rank r publishes its Σ v·w[y] of exchange number `seq` in slot [seq % kXDepth][r] of EVERY rank's block and then
+// releases flags[seq % kXDepth][r] = seq; a consumer spins on the N flags of its own block and adds the N values in
+// rank order, so every rank divides by the bit-identical total.  Depth 8: a rank may run up to 7 exchanges ahead of
+// the slowest reader before it would overwrite an unread slot (a reader that finds a newer sequence number reports it).
+constexpr int kXDepth = 8;
+constexpr int kXMaxRanks = 16;
+struct XchgBlock {
+    double slots[kXDepth][kXMaxRanks];
+    unsigned int flags[kXDepth][kXMaxRanks];
+    unsigned long long seq;        // exchanges completed by THIS rank (advanced by the last CTA of each launch)
+    unsigned long long errors;     // time-outs / overruns seen by this rank's readers
+};
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -235,6 +252,7 @@ struct BinAcc {
         else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(kThreads) : "memory");
     }
     unsigned short* cnt16;
+    unsigned short* mine;      // PRIV: cnt16 + threadIdx.x (this thread's counter of bin 0)
     unsigned int* bins32;
     unsigned long long* direct;
     int nb;
@@ -247,6 +265,7 @@ struct BinAcc {
         direct = global_bins;
         if constexpr (PRIV) {
             cnt16 = reinterpret_cast<unsigned short*>(smem);
+            mine = cnt16 + threadIdx.x;
             uint32_t* z = reinterpret_cast<uint32_t*>(smem);
             for (int i = threadIdx.x; i < nb * kThreads / 2; i += kThreads) z[i] = 0u;
         } else {
@@ -257,11 +276,23 @@ struct BinAcc {
     }
     __device__ __forceinline__ void add(int key, unsigned int n = 1u) {
         if constexpr (PRIV) {
-            unsigned short* c = cnt16 + key * kThreads + threadIdx.x;
+            unsigned short* c = mine + key * kThreads;
             *c = static_cast<unsigned short>(*c + n);
         } else {
             if (reps) atomicAdd(bins32 + ((threadIdx.x >> 5) & (reps - 1)) * nb + key, n);
             else atomicAdd(direct + key, static_cast<unsigned long long>(n));
+        }
+    }
+    // Shared mode with warp aggregation: the lanes of a warp that hit the SAME bin with the same increment merge into
+    // one shared-memory atomic issued by the lowest such lane (match.any + popc) — blocky label maps put whole warps on
+    // one or two bins, which would otherwise serialise on one address.  Callable from divergent code (the match runs
+    // over the lanes that are converged here).  Private mode: a plain private update.
+    __device__ __forceinline__ void add_agg(int key, unsigned int n = 1u) {
+        if constexpr (PRIV) {
+            add(key, n);
+        } else {
+            const unsigned int peers = __match_any_sync(__activemask(), (key << 4) | static_cast<int>(n & 15u));
+            if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) add(key, n * static_cast<unsigned int>(__popc(peers)));
         }
     }
     static __host__ __device__ int smem_bytes(int nbins, int replicas = kWarps) {

@@ -60,19 +60,18 @@ class _FusedCE(torch.autograd.Function):
     def backward(ctx, grad_output):
         d = ctx.dlogits
         if d is None:
+            if getattr(ctx, "consumed", False):
+                raise RuntimeError("FusedCrossEntropyLoss: the gradient buffer of this forward was already handed to autograd "
+                                   "(a second backward through the same loss, e.g. retain_graph=True, is not supported: "
+                                   "call the criterion again)")
             raise RuntimeError("FusedCrossEntropyLoss: backward called but the forward ran without grad")
         ctx.dlogits = None
-        mode = ctx.module.grad_scale_mode
-        if mode == "check" and torch.cuda.is_current_stream_capturing():
-            mode = "scale"            # no host read inside a CUDA-graph capture: multiply on the device instead
-        if mode == "check":
-            # `loss.backward()` feeds exactly 1.0 (train.py:125); the reference loop has already
-            # synchronised on loss.item(), so reading 4 bytes here costs no extra bubble.
-            if float(grad_output) != 1.0:
-                ops.scale_inplace(d, grad_output.to(torch.float32).reshape(1))
-        elif mode == "scale":
+        ctx.consumed = True
+        if ctx.module.grad_scale_mode != "unit":
+            # dlogits *= grad_output on the device; the kernel returns at once when grad_output == 1.0, which is what
+            # `loss.backward()` feeds (train.py:125) — no host read, no synchronisation, graph-capturable
             ops.scale_inplace(d, grad_output.to(torch.float32).reshape(1))
-        # mode == "unit": trust the caller that grad_output == 1
+        # mode == "unit": trust the caller that grad_output == 1 (saves the ~3 us launch)
         return ctx.restore(d), None, None, None
 
 
@@ -82,7 +81,10 @@ class FusedCrossEntropyLoss(nn.Module):
     Extras over the reference signature (all optional):
       confusion      a ``cvcs_b200.metrics.MulticlassConfusionMatrix`` to update in the same pass
       return_argmax  keep the argmax map of the last call in ``self.last_argmax`` (uint8)
-      grad_scale_mode  'check' (default) | 'unit' | 'scale' — how ``grad_output`` is honoured
+      grad_scale_mode  'check' (default) = 'scale': dlogits *= grad_output by a kernel that exits immediately when
+                     grad_output == 1 (no host read); 'unit': skip even that launch (caller guarantees 1.0)
+      exchange       a ``cvcs_b200.shard.WeightExchange``: the 'mean' divides by Σ v·w[y] over ALL ranks' batches, exchanged
+                     inside the fused kernel over NVLink (no all-reduce, no extra launch)
       strict         synchronise after every call and raise IndexError on out-of-bounds labels
                      (default: the loss is NaN-poisoned and ``check_errors()`` raises)
     Targets may be int64 (as the reference passes) or uint8 (as the masks are stored: skips the
@@ -91,7 +93,7 @@ class FusedCrossEntropyLoss(nn.Module):
 
     def __init__(self, weight: Optional[torch.Tensor] = None, ignore_index: int = -100, reduction: str = "mean",
                  label_smoothing: float = 0.0, confusion=None, return_argmax: bool = False,
-                 grad_scale_mode: str = "check", strict: bool = False):
+                 grad_scale_mode: str = "check", strict: bool = False, exchange=None):
         super().__init__()
         if reduction != "mean" or label_smoothing != 0.0:
             raise NotImplementedError("the reference only uses reduction='mean', label_smoothing=0 (utils.py:230,238)")
@@ -103,44 +105,43 @@ class FusedCrossEntropyLoss(nn.Module):
         self.return_argmax = return_argmax
         self.grad_scale_mode = grad_scale_mode
         self.strict = strict
+        self.exchange = exchange
         self.last_argmax: Optional[torch.Tensor] = None
         self.last_sums: Optional[torch.Tensor] = None  # f64[3] {Σ w·nll, Σ w, #out-of-bounds}
+        self.last_total_weight: Optional[torch.Tensor] = None  # f64[2] {Σ v·w[y] (global), 1/Σ} when data dependent
         self._w32: Optional[torch.Tensor] = None
-        self._prefetched = None   # (target tensor, num_classes, f64[2] total weight, ready event)
+        self._w32_key = None
+        self._prefetched = None   # (target tensor, its version, num_classes, f64[2] total weight, ready event, u8 labels)
         self._side: Optional[torch.cuda.Stream] = None
 
     # -- helpers -------------------------------------------------------------------------------------
     def _weight_f32(self, dev: torch.device) -> Optional[torch.Tensor]:
         if self.weight is None:
             return None
-        if self._w32 is None or self._w32.device != dev:
+        # `weight` is a registered buffer: load_state_dict / in-place edits must reach the kernel
+        key = (dev, self.weight.data_ptr(), self.weight._version)
+        if self._w32 is None or self._w32_key != key:
             self._w32 = self.weight.to(device=dev, dtype=torch.float32).contiguous()
+            self._w32_key = key
         return self._w32
 
     def prefetch_total_weight(self, target: torch.Tensor, num_classes: int) -> None:
-        """Optional: start the label pre-pass (K4, Σ v·w[y]) for ``target`` on a side stream NOW — e.g. right
-        after the batch is loaded, while the model's forward pass runs — so that the next ``forward`` with this
-        same target tensor finds the 'mean' divisor ready instead of computing it in front of the fused kernel."""
-        if not target.is_cuda or target.dtype not in (torch.int64, torch.uint8):
+        """Optional, int64 labels: start the label pre-pass (Σ v·w[y] + the byte copy of the labels) for ``target`` on a
+        side stream NOW — e.g. right after the batch is loaded, while the model's forward pass runs — so that the next
+        ``forward`` with this same, unmodified target tensor finds it done.  (uint8 labels need no pre-pass launch at
+        all: the fused kernel sums the weights itself.)"""
+        if not target.is_cuda or target.dtype != torch.int64 or num_classes > 254:
             return
         dev = target.device
         t = target.reshape(target.shape[0], -1, 1) if target.dim() != 3 else target
         if self._side is None or self._side.device != dev:
             self._side = torch.cuda.Stream(device=dev)
         self._side.wait_stream(torch.cuda.current_stream(dev))     # the labels must have been produced
-        tw = torch.empty(2, dtype=torch.float64, device=dev)
-        t8 = None
         with torch.cuda.stream(self._side):
-            if t.dtype == torch.int64 and num_classes <= 254:
-                _, t8 = ops.labels_prepare(t.contiguous(), num_classes, self.ignore_index, self._weight_f32(dev), tw)
-                t8.record_stream(self._side)
-            else:
-                ops.label_hist(t.contiguous(), num_classes, self.ignore_index, hist=None, weight=self._weight_f32(dev),
-                               total_weight_out=tw)
+            tw, t8 = ops.labels_prepare(t.contiguous(), num_classes, self.ignore_index, self._weight_f32(dev))
             ev = torch.cuda.Event()
             ev.record(self._side)
-        tw.record_stream(self._side)
-        self._prefetched = (target, num_classes, tw, ev, t8)
+        self._prefetched = (target, target._version, num_classes, tw, ev, t8)
 
     def _run(self, logits: torch.Tensor, target: torch.Tensor, want_grad: bool):
         if not logits.is_cuda:
@@ -157,36 +158,57 @@ class FusedCrossEntropyLoss(nn.Module):
         if w is not None and w.numel() != C:
             raise RuntimeError(f"weight tensor should be defined either for all {C} classes or no classes "
                                f"but got weight tensor of shape: {list(w.shape)}")
-        inv_tw, inv_tw_dev = 0.0, None
-        ii = self.ignore_index
-        if want_grad:
-            if w is None and t.dtype == torch.uint8 and not (0 <= self.ignore_index <= 255):
-                inv_tw = 1.0 / float(B * H * W)  # nothing can be ignored: Σ v·w is the pixel count
-            elif self._prefetched is not None and self._prefetched[0] is target and self._prefetched[1] == C:
-                _, _, tw, ev, t8 = self._prefetched               # pre-pass already running / done on the side stream
-                torch.cuda.current_stream(dev).wait_event(ev)
-                inv_tw_dev = tw[1:]
-                if t8 is not None:
-                    t, ii = t8.reshape(t.shape), 255
-                self._prefetched = None
-            elif t.dtype == torch.int64 and C <= 254:
-                # the reference passes mask.type(torch.long): one pass over the 8-byte labels yields Σ v·w[y] AND a
-                # byte copy (255 = ignored, 254 = out of range) for the fused kernel to read instead
-                tw, t = ops.labels_prepare(t, C, self.ignore_index, w)
-                inv_tw_dev, ii = tw[1:], 255
-            else:
-                tw = torch.empty(2, dtype=torch.float64, device=dev)
-                ops.label_hist(t, C, self.ignore_index, hist=None, weight=w, total_weight_out=tw)
-                inv_tw_dev = tw[1:]
-        argmax = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if (self.return_argmax and C <= 256) else None
         conf = None
         if self.confusion is not None:
+            # the fused update filters labels with THIS criterion's ignore_index: a metric built with another one
+            # would silently count different pixels than its own update() does
+            m_ign = self.confusion.ignore_index
+            mine = self.ignore_index if 0 <= self.ignore_index < C else None
+            if (m_ign if (m_ign is not None and 0 <= m_ign < C) else None) != mine:
+                raise RuntimeError(f"FusedCrossEntropyLoss(ignore_index={self.ignore_index}) cannot update a confusion matrix "
+                                   f"built with ignore_index={m_ign}: the fused pass drops the loss's ignored pixels")
             conf = self.confusion._state_for(dev, C)
-        loss_out, sums, dlogits = ops.ce_fused(x, t, w, ii, want_grad=want_grad,
-                                               inv_total_weight=inv_tw, inv_total_weight_dev=inv_tw_dev,
-                                               argmax=argmax, confmat=conf)
+        xchg = self.exchange.handle_for(dev) if self.exchange is not None else None
+        ii = self.ignore_index
+        mode, inv_tw, tw = "given", 0.0, None
+        if t.dtype == torch.int64 and C <= 254 and want_grad:
+            # the reference passes mask.type(torch.long): ONE pass over the 8-byte labels yields Σ v·w[y] and a byte copy
+            # (255 = ignored, 254 = out of range) that the fused kernel reads instead (1 B/px instead of 8 B/px)
+            pf = self._prefetched
+            if pf is not None and pf[0] is target and pf[1] == target._version and pf[2] == C:
+                _, _, _, tw, ev, t8 = pf                          # already running / done on the side stream
+                cur = torch.cuda.current_stream(dev)
+                cur.wait_event(ev)
+                tw.record_stream(cur)                             # consumed on this stream: keep the allocator away
+                t8.record_stream(cur)
+                t8 = t8.reshape(t.shape)
+            else:
+                tw, t8 = ops.labels_prepare(t, C, self.ignore_index, w)
+            self._prefetched = None
+            t, ii = t8, 255
+        if want_grad:
+            if xchg is not None:
+                mode = "kernel"                                   # global Σw: exchanged inside the kernel
+            elif tw is not None:
+                pass                                              # int64 labels, single GPU: 1/Σ from the pre-pass
+            elif w is None and not (0 <= ii <= 255):
+                inv_tw = 1.0 / float(B * H * W)                   # nothing can be ignored: Σ v·w is the pixel count
+            else:
+                mode = "kernel"                                   # uint8 labels: the kernel sums the weights itself
+        argmax = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if (self.return_argmax and C <= 256) else None
+        if mode == "kernel":
+            tw = torch.empty(2, dtype=torch.float64, device=dev)
+            loss_out, sums, dlogits = ops.ce_fused(x, t, w, ii, want_grad=True, total_weight="kernel", xchg=xchg,
+                                                   total_weight_out=tw, argmax=argmax, confmat=conf)
+        else:
+            loss_out, sums, dlogits = ops.ce_fused(x, t, w, ii, want_grad=want_grad, inv_total_weight=inv_tw,
+                                                   inv_total_weight_dev=tw[1:] if (want_grad and tw is not None) else None,
+                                                   argmax=argmax, confmat=conf)
         self.last_argmax = argmax
         self.last_sums = sums
+        self.last_total_weight = tw if want_grad else None
+        if self.confusion is not None:
+            self.confusion._note_bad_labels(sums)
         if self.strict:
             self.check_errors()
         loss = loss_out.reshape(())

@@ -124,16 +124,33 @@ class MulticlassConfusionMatrix:
     __call__ = update
 
     # -- compute ---------------------------------------------------------------------------------
+    def _note_bad_labels(self, loss_sums: torch.Tensor) -> None:
+        """The fused loss kernel counts labels outside [0, C) that are not ignore_index in loss_sums[2]; feed them into
+        this metric's validate_args status so that compute() raises as update() would have (no host read here)."""
+        if self._s["status"] is not None:
+            self._s["status"].add_(loss_sums[2:3].to(torch.int64))
+
     def sync(self, group=None) -> None:
-        """Sum the state over all ranks (NCCL all-reduce of C*C int64; latency-bound)."""
+        """COLLECTIVE: sum the state over all ranks of ``group`` (one all-reduce of C*C int64 plus the status word).
+        Every rank of the group must call it exactly once per evaluation pass, and only when the ranks evaluated
+        DISJOINT tile sets (``cvcs_b200.shard.local_tiles``): ranks that each evaluated the full validation set would
+        count every pixel world_size times.  A rank-0-only ``validate()`` must not call it (the others never arrive)."""
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            cm = self._s["confmat"]
-            if cm is None:
-                dev = self._device or torch.device("cuda", torch.cuda.current_device())
-                cm = self._state_for(dev)
-            dist.all_reduce(cm, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(self._s["status"], op=dist.ReduceOp.SUM, group=group)
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        cm = self._s["confmat"]
+        if cm is None and (self._s["host"] is not None or not torch.cuda.is_available()):
+            # state restored from a checkpoint and not touched on a GPU since (or a CPU-only process, e.g. the gloo
+            # tests): reduce the host copy
+            if self._s["host"] is None:
+                self._s["host"] = torch.zeros((self.num_classes, self.num_classes), dtype=torch.int64)
+            dist.all_reduce(self._s["host"], op=dist.ReduceOp.SUM, group=group)
+            return
+        if cm is None:
+            dev = self._device or torch.device("cuda", torch.cuda.current_device())
+            cm = self._state_for(dev)
+        dist.all_reduce(cm, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self._s["status"], op=dist.ReduceOp.SUM, group=group)
 
     def compute(self) -> torch.Tensor:
         """int64[C,C] on the CPU (normalize None) or the float32 normalised matrix (NaN -> 0)."""
@@ -259,12 +276,17 @@ def print_metrics(confusion, silent=False, labels=GID15_LABELS):
 
 # ---- evaluation loops (utils.py:59-126) -----------------------------------------------------------
 def eval_model(net, Loader_validation, device, batch_size=1, show_progress=False, ignore_background=False,
-               num_classes: int = 16, sync_ranks: bool = True):
+               num_classes: int = 16, sync_ranks: bool = False):
     """Same contract as the reference's ``utils.eval_model`` (utils.py:59-103): returns
     ``(flat_confusion_metric, normalized_confusion_metric)``.  ``num_classes`` defaults to the 16
     the reference hard-codes (utils.py:77-78).  Differences, all internal: logits stay on the
     GPU, argmax + confusion run fused (K1, forward only), any ``batch_size`` works, and the two
-    returned metrics are views of one state."""
+    returned metrics are views of one state.
+
+    ``sync_ranks`` (default False, the reference is single-process): pass True ONLY when torch.distributed is initialised,
+    EVERY rank calls eval_model, and ``Loader_validation`` hands each rank a disjoint share of the tiles — then the
+    returned metrics hold the global counts (``MulticlassConfusionMatrix.sync``, a collective).  With the default each
+    rank returns what it evaluated itself, which for an unsharded loader is exactly the single-process result."""
     net.eval()
     ignored_index = 0 if ignore_background else None
     flat = MulticlassConfusionMatrix(num_classes=num_classes, ignore_index=ignored_index, device=device)

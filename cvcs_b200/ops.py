@@ -133,14 +133,94 @@ def total_weight(hist: torch.Tensor, weight: Optional[torch.Tensor], num_classes
 
 
 # ---- K1 ------------------------------------------------------------------------------------------
+class Exchange:
+    """cvcs_xchg: this rank's Σw exchange block plus the peers' blocks (CUDA IPC mappings).  Built by
+    ``cvcs_b200.shard.WeightExchange`` for one-process-per-GPU jobs; tests wire several handles of one process together
+    with ``set_peer`` / play a peer with ``poke``."""
+
+    def __init__(self, world: int, rank: int, device: Optional[torch.device] = None):
+        self._h = ctypes.c_void_p()
+        self.world, self.rank = int(world), int(rank)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(self.device):
+            check(lib.cvcs_xchg_create(ctypes.byref(self._h), self.world, self.rank))
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        if not self._h:
+            raise RuntimeError("cvcs_b200.Exchange: already closed")
+        return self._h
+
+    def local_handle(self) -> bytes:
+        buf = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            check(lib.cvcs_xchg_local_handle(self.handle, buf))
+        return bytes(buf)
+
+    def open_peer(self, peer_rank: int, handle: bytes) -> None:
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        with torch.cuda.device(self.device):
+            check(lib.cvcs_xchg_open_peer(self.handle, int(peer_rank), buf))
+
+    def set_peer(self, peer_rank: int, other: "Exchange") -> None:
+        check(lib.cvcs_xchg_set_peer(self.handle, int(peer_rank), lib.cvcs_xchg_local_block(other.handle)))
+
+    def state(self) -> Tuple[int, int]:
+        """(exchanges completed by this rank, time-outs / overruns its kernels saw) — synchronises the device."""
+        seq, err = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        with torch.cuda.device(self.device):
+            check(lib.cvcs_xchg_state(self.handle, ctypes.byref(seq), ctypes.byref(err)))
+        return int(seq.value), int(err.value)
+
+    def poke(self, as_rank: int, seq: int, value: float) -> None:
+        with torch.cuda.device(self.device):
+            check(lib.cvcs_xchg_poke(self.handle, int(as_rank), int(seq), float(value), _stream(self.device)))
+
+    def close(self) -> None:
+        if self._h:
+            lib.cvcs_xchg_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _check_k1_buffers(logits, Cc, weight, dlogits, argmax, confmat, loss_sums, loss_out, B, H, W):
+    """Cheap host-side checks of everything that crosses the C-ABI as a raw pointer (a wrong dtype or size would be a
+    silent out-of-bounds access on the GPU)."""
+    if weight is not None and (weight.dtype != torch.float32 or weight.numel() != Cc or not weight.is_contiguous()):
+        raise RuntimeError(f"weight tensor should be a contiguous float32 tensor of size {Cc}, got {weight.dtype} {tuple(weight.shape)}")
+    if confmat is not None and (confmat.dtype != torch.int64 or confmat.numel() != Cc * Cc or not confmat.is_contiguous()):
+        raise RuntimeError(f"confmat must be a contiguous int64 [{Cc},{Cc}] tensor, got {confmat.dtype} {tuple(confmat.shape)}")
+    if argmax is not None:
+        if argmax.dtype not in (torch.uint8, torch.int64) or argmax.numel() != B * H * W or not argmax.is_contiguous():
+            raise RuntimeError(f"argmax must be a contiguous uint8 / int64 tensor of {B * H * W} elements, got {argmax.dtype} {tuple(argmax.shape)}")
+    if dlogits is not None:
+        if dlogits.dtype != logits.dtype or dlogits.shape != logits.shape or dlogits.stride() != logits.stride():
+            raise RuntimeError("dlogits must have the dtype, shape and memory format of logits")
+    if loss_sums is not None and (loss_sums.dtype != torch.float64 or loss_sums.numel() != 3 or not loss_sums.is_contiguous()):
+        raise RuntimeError("loss_sums must be a contiguous float64 tensor of 3 elements")
+    if loss_out is not None and (loss_out.dtype != torch.float32 or loss_out.numel() != 1):
+        raise RuntimeError("loss_out must be a float32 tensor of 1 element")
+
+
 def ce_fused(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor] = None,
              ignore_index: int = -100, *, want_grad: bool = True, inv_total_weight: float = 0.0,
              inv_total_weight_dev: Optional[torch.Tensor] = None, dlogits: Optional[torch.Tensor] = None,
              argmax: Optional[torch.Tensor] = None, confmat: Optional[torch.Tensor] = None,
-             loss_sums: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None):
+             loss_sums: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None,
+             total_weight: str = "given", xchg: Optional[Exchange] = None,
+             total_weight_out: Optional[torch.Tensor] = None):
     """One fused pass. logits [B,C,H,W] f32/bf16 (contiguous or channels_last), target [B,H,W]
-    u8/i64.  Returns (loss_out f32[1], loss_sums f64[3], dlogits or None)."""
-    dev = _need_cuda(logits, target, weight, inv_total_weight_dev, dlogits, argmax, confmat, loss_sums, loss_out)
+    u8/i64.  Returns (loss_out f32[1], loss_sums f64[3], dlogits or None).
+
+    total_weight="given": the 'mean' divisor comes from inv_total_weight / inv_total_weight_dev (cvcs_ce_fused).
+    total_weight="kernel": the kernel computes it from the labels itself — and, with ``xchg``, over all ranks' labels —
+    before it writes the first gradient (cvcs_ce_fused_tw); ``total_weight_out`` f64[2] receives {Σ, 1/Σ}."""
+    dev = _need_cuda(logits, target, weight, inv_total_weight_dev, dlogits, argmax, confmat, loss_sums, loss_out, total_weight_out)
     if logits.dim() != 4:
         raise RuntimeError(f"cvcs_b200.ce_fused expects [B,C,H,W] logits, got {tuple(logits.shape)}")
     B, Cc, H, W = logits.shape
@@ -154,12 +234,28 @@ def ce_fused(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.
         loss_sums = torch.empty(3, dtype=torch.float64, device=dev)
     if loss_out is None:
         loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+    _check_k1_buffers(logits, Cc, weight, dlogits if want_grad else None, argmax, confmat, loss_sums, loss_out, B, H, W)
+    if inv_total_weight_dev is not None and inv_total_weight_dev.dtype != torch.float64:
+        raise RuntimeError("inv_total_weight_dev must be float64")
     with torch.cuda.device(dev):
-        check(lib.cvcs_ce_fused(logits.data_ptr(), _tag(logits), layout, target.data_ptr(), _tag(target),
-                                _ptr(weight), ignore_index, B, Cc, H, W, float(inv_total_weight),
-                                _ptr(inv_total_weight_dev), _ptr(dlogits) if want_grad else None, _ptr(argmax),
-                                _tag(argmax) if argmax is not None else _lib.U8, _ptr(confmat),
-                                loss_sums.data_ptr(), loss_out.data_ptr(), workspace(dev).data_ptr(), _stream(dev)))
+        if total_weight == "kernel":
+            if total_weight_out is None:
+                total_weight_out = torch.empty(2, dtype=torch.float64, device=dev)
+            elif total_weight_out.dtype != torch.float64 or total_weight_out.numel() != 2:
+                raise RuntimeError("total_weight_out must be a float64 tensor of 2 elements")
+            check(lib.cvcs_ce_fused_tw(logits.data_ptr(), _tag(logits), layout, target.data_ptr(), _tag(target),
+                                       _ptr(weight), ignore_index, B, Cc, H, W, xchg.handle if xchg is not None else None,
+                                       total_weight_out.data_ptr(), _ptr(dlogits) if want_grad else None, _ptr(argmax),
+                                       _tag(argmax) if argmax is not None else _lib.U8, _ptr(confmat),
+                                       loss_sums.data_ptr(), loss_out.data_ptr(), workspace(dev).data_ptr(), _stream(dev)))
+        elif total_weight == "given":
+            check(lib.cvcs_ce_fused(logits.data_ptr(), _tag(logits), layout, target.data_ptr(), _tag(target),
+                                    _ptr(weight), ignore_index, B, Cc, H, W, float(inv_total_weight),
+                                    _ptr(inv_total_weight_dev), _ptr(dlogits) if want_grad else None, _ptr(argmax),
+                                    _tag(argmax) if argmax is not None else _lib.U8, _ptr(confmat),
+                                    loss_sums.data_ptr(), loss_out.data_ptr(), workspace(dev).data_ptr(), _stream(dev)))
+        else:
+            raise ValueError(f"total_weight must be 'given' or 'kernel', got {total_weight!r}")
     return loss_out, loss_sums, (dlogits if want_grad else None)
 
 

@@ -110,6 +110,45 @@ def global_confmat(confmat: torch.Tensor, group=None) -> torch.Tensor:
     return confmat
 
 
+class WeightExchange:
+    """Collective (1) without a collective call: the per-step global Σ v·w[y] is exchanged INSIDE the fused loss kernel
+    (``ops.ce_fused(..., total_weight="kernel", xchg=...)`` / ``FusedCrossEntropyLoss(exchange=...)``).  Each rank owns a
+    small device block; here the blocks' CUDA IPC handles travel once through ``all_gather_object`` and every rank maps
+    its peers' blocks (NVLink peer access).  Afterwards a step costs one kernel launch: rank r's kernel stores its sum
+    into every rank's block and adds the N values it finds in its own, in rank order.
+
+    Every rank must run the same sequence of exchanging launches (as with any collective).  COLLECTIVE constructor."""
+
+    def __init__(self, group=None, device=None):
+        from . import ops
+        self.group = group
+        self.rank, self.world = world_info(group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.x = ops.Exchange(self.world, self.rank, self.device)
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.x.local_handle(), group=group)
+            for q, h in enumerate(handles):
+                if q != self.rank:
+                    self.x.open_peer(q, h)
+            dist.barrier(group)            # nobody launches before every mapping exists
+
+    def handle_for(self, dev: torch.device):
+        if torch.device(dev) != self.device:
+            raise RuntimeError(f"WeightExchange lives on {self.device}, tensors on {dev}")
+        return self.x
+
+    def state(self):
+        """(exchanges completed, time-outs / overruns seen) on this rank — synchronises."""
+        return self.x.state()
+
+    def close(self):
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)       # peers may still be reading / writing this rank's block
+        self.x.close()
+
+
 # ---- a sharded evaluation / loss pass over scenes ---------------------------------------------------------------
 class ShardedScenePass:
     """Tiles a list of scenes, runs ``logits_fn`` on this rank's tile batches and accumulates the

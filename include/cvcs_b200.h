@@ -100,7 +100,10 @@ enum cvcs_option {
     CVCS_OPT_TMA_CTAS = 4,   /* CTAs per SM the TMA variant sizes its stages for (0 = default 2; 1..4)      */
     CVCS_OPT_TILE_CTAS = 5,  /* K5: CTAs per SM of the persistent grid (0 = default; 1..8)                  */
     CVCS_OPT_RESERVE_SMS = 6, /* K1: SMs left free (e.g. for an NCCL kernel that must run concurrently); 0..32   */
-    CVCS_OPT_COUNT = 7
+    CVCS_OPT_PDL = 7,        /* K1 (TMA variant): 1 = launch with programmatic stream serialization (the kernel's
+                                prologue overlaps the tail of the previous kernel in the stream; it waits for that
+                                kernel before reading global memory)                                                  */
+    CVCS_OPT_COUNT = 8
 };
 int cvcs_set_option(int option, int value);
 
@@ -153,6 +156,40 @@ int cvcs_ce_fused(const void* logits_dev, int logits_dtype, int layout, const vo
                   unsigned long long* confmat_dev, double* loss_sums_dev, float* loss_out_dev,
                   void* workspace_dev, void* stream);
 
+/* ---- K1 with the total weight computed inside the kernel, and exchanged across GPUs -----------------------------
+ * nn.CrossEntropyLoss's 'mean' (utils.py:230,238) divides every gradient by Σ_i v_i w[y_i] of the whole batch — with
+ * data-parallel ranks, of ALL ranks' batches (SURVEY §8e collective (1)).  cvcs_ce_fused_tw needs no cvcs_label_hist
+ * launch and no all-reduce in front of it: the kernel's CTAs first sum the weights over the (u8) labels, meet at a
+ * grid-wide barrier, and — when `xchg` spans several ranks — one thread stores this rank's sum into every peer's
+ * exchange block over NVLink while every CTA waits for the peers' sums in its own block and adds them in rank order
+ * (bit-identical total on every rank).  One launch per step; the collective is a handful of 8-byte peer stores.
+ *   xchg                  nullable (single GPU); see below
+ *   total_weight_out_dev  nullable f64[2], overwritten with {Σ (global), 1/Σ}
+ * Everything else as cvcs_ce_fused.  Shapes the TMA-staged kernel does not take (int64 labels, odd sizes, C > 21) run
+ * as cvcs_label_hist + cvcs_ce_fused internally on one GPU (total_weight_out_dev required) and are refused with
+ * CVCS_ERR_UNSUPPORTED across GPUs.  Every rank of an exchange must make the same sequence of calls. */
+typedef struct cvcs_xchg cvcs_xchg;
+int cvcs_ce_fused_tw(const void* logits_dev, int logits_dtype, int layout, const void* target_dev,
+                     int target_dtype, const float* weight_dev, long long ignore_index, int B, int C,
+                     int H, int W, cvcs_xchg* xchg, double* total_weight_out_dev, void* dlogits_dev,
+                     void* argmax_dev, int argmax_dtype, unsigned long long* confmat_dev,
+                     double* loss_sums_dev, float* loss_out_dev, void* workspace_dev, void* stream);
+
+/* Exchange handle: a small device block on this rank (cudaMalloc) plus the peers' blocks mapped into this process.
+ * One process per GPU: create, pass cvcs_xchg_local_handle's 64 bytes (a cudaIpcMemHandle_t) to the other ranks with
+ * whatever transport the host program has (torch.distributed all_gather_object in cvcs_b200.shard), open each peer's.
+ * Several GPUs in one process: cvcs_xchg_set_peer with the other handle's cvcs_xchg_local_block (peer access enabled
+ * by the caller).  cvcs_xchg_state reads {exchanges completed, time-outs/overruns seen}; cvcs_xchg_poke plays another
+ * rank's part of exchange number `seq` (tests). */
+int cvcs_xchg_create(cvcs_xchg** out, int world, int rank);
+int cvcs_xchg_local_handle(cvcs_xchg* x, unsigned char* handle_out64);
+int cvcs_xchg_open_peer(cvcs_xchg* x, int peer_rank, const unsigned char* handle64);
+int cvcs_xchg_set_peer(cvcs_xchg* x, int peer_rank, void* block_dev);
+void* cvcs_xchg_local_block(cvcs_xchg* x);
+int cvcs_xchg_state(cvcs_xchg* x, unsigned long long* seq_out, unsigned long long* errors_out);
+int cvcs_xchg_poke(cvcs_xchg* x, int as_rank, unsigned long long seq, double value, void* stream);
+int cvcs_xchg_destroy(cvcs_xchg* x);
+
 /* ---- K1, metrics mode: argmax + confusion matrix straight from logits, no softmax / loss -----------
  * What utils.eval_model needs per tile (utils.py:88-94: torch.max + two MulticlassConfusionMatrix
  * updates): one read of the logits, the u8 / i64 argmax map (nullable) and the C x C update
@@ -163,7 +200,7 @@ int cvcs_eval_fused(const void* logits_dev, int logits_dtype, int layout, const 
                     void* argmax_dev, int argmax_dtype, unsigned long long* confmat_dev,
                     unsigned long long* status_dev, void* workspace_dev, void* stream);
 
-/* x[i] *= *scale_dev, in place (x: CVCS_F32 or CVCS_BF16). */
+/* x[i] *= *scale_dev, in place (x: CVCS_F32 or CVCS_BF16).  Returns without touching x when *scale_dev == 1.0f. */
 int cvcs_scale_inplace(void* x_dev, int dtype, long long n, const float* scale_dev, void* stream);
 
 /* ---- K2: argmax over the class dimension -------------------------------------------- */

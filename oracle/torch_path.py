@@ -206,3 +206,64 @@ def macro_mean(scores, excluded) -> float:
 def overall_accuracy(confusion: torch.Tensor) -> float:
     C = confusion.shape[1]
     return sum(confusion[i, i].item() for i in range(C)) / torch.sum(confusion).item()
+
+
+# ---- BASELINE.json configs[0]: the reference's own CPU-runnable case ------------------------------------------
+def unet_like(num_classes: int) -> nn.Module:
+    """A restatement of the reference's U-Net variant (nets.py:117-199 `Urnetv2`, blocks.py:8-50): five encoder
+    levels of two 3x3 conv + BatchNorm + ReLU (64..1024 channels, 2x2 max-pool between levels), four
+    transposed-conv upsamplings each followed by two 3x3 conv + ReLU + BatchNorm on the concatenated skip, and a
+    final 1x1 conv.  Same layer sequence and widths, hence the same parameter count (31.04 M for 7 classes); used
+    only as the timed CPU workload of cfg1 — the network itself is out of this repo's scope."""
+
+    def enc(cin, cout):
+        return [nn.Conv2d(cin, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.ReLU()]
+
+    def dec(cin, cout):
+        return nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.ReLU(), nn.BatchNorm2d(cout),
+                             nn.Conv2d(cout, cout, 3, padding=1), nn.ReLU(), nn.BatchNorm2d(cout))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            widths = [64, 128, 256, 512, 1024]
+            self.down = nn.ModuleList()
+            cin = 3
+            for i, wd in enumerate(widths):
+                layers = ([nn.MaxPool2d(2, 2)] if i else []) + enc(cin, wd) + enc(wd, wd)
+                self.down.append(nn.Sequential(*layers))
+                cin = wd
+            self.up = nn.ModuleList(nn.ConvTranspose2d(w2, w1, 2, stride=2) for w1, w2 in zip(widths[-2::-1], widths[:0:-1]))
+            self.mix = nn.ModuleList(dec(2 * w1, w1) for w1 in widths[-2::-1])
+            self.head = nn.Conv2d(widths[0], num_classes, 1)
+
+        def forward(self, x):
+            skips = []
+            for blk in self.down:
+                x = blk(x)
+                skips.append(x)
+            skips.pop()
+            for up, mix in zip(self.up, self.mix):
+                x = mix(torch.cat((skips.pop(), up(x)), 1))
+            return self.head(x)
+
+    return Net()
+
+
+def cfg1_step(seed: int = 0, num_classes: int = 7, batch: int = 2, size: int = 512):
+    """One step of cfg1 the way train.py / utils.eval_model run it on the host: u8 RGB tiles -> float32 (train.py:121),
+    segmenter forward, CrossEntropyLoss(ignore_index=0) (utils.py:223-230 with ignore_background), per-tile
+    torch.max + confusion update (utils.py:88-94), mean IoU (utils.py:301-346)."""
+    torch.manual_seed(seed)
+    net = unet_like(num_classes).eval()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(0, 256, (batch, 3, size, size), generator=g, dtype=torch.uint8)
+    y = torch.randint(0, num_classes, (batch, size, size), generator=g, dtype=torch.uint8)
+    with torch.no_grad():
+        logits = net(x.type(torch.float32))
+        loss = ce_loss_only(logits, y, None, 0)
+    flat, _, _ = eval_tiles(logits, y, num_classes, ignore_background=True)
+    cm = flat.compute()
+    scores, excluded = class_scores(cm, "iou")
+    return {"model": "U-Net variant (restated nets.py Urnetv2)", "params": sum(p.numel() for p in net.parameters()),
+            "loss": float(loss), "miou": macro_mean(scores, excluded)}

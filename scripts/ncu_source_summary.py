@@ -10,6 +10,9 @@ hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
 col = {n: i for i, n in enumerate(hdr)}
 data = rows[hdr_i + 1:]
+# several launches / pages in one export: keep the first kernel's rows
+end = next((i for i, r in enumerate(data) if not r or r[0] in ("Kernel Name", "Address")), len(data))
+data = [r for r in data[:end] if len(r) == len(hdr)]
 tot_inst = sum(int(r[col["Instructions Executed"]]) for r in data)
 tot_thr = sum(int(r[col["Thread Instructions Executed"]]) for r in data)
 tot_samp = sum(int(r[col["# Samples"]]) for r in data)

@@ -300,25 +300,36 @@ def test_host_buffer_entry_point(dtype, pinned):
 
 
 def test_prefetched_total_weight_gives_identical_results():
-    """crit.prefetch_total_weight(target) moves the K4 pre-pass to a side stream ahead of time; loss and
-    gradients are bit-identical to the in-line pre-pass."""
+    """crit.prefetch_total_weight(target) moves the int64-label pre-pass (Σw + byte labels) to a side stream ahead of
+    time; loss and gradients are bit-identical to the in-line pre-pass, and a target that was modified in place after
+    the prefetch (label remap, a reused staging buffer) does not get the stale Σw / stale byte labels."""
     from cvcs_b200.loss import FusedCrossEntropyLoss
     torch.manual_seed(3)
     C = 7
     w = torch.rand(C) + 0.5
     crit = FusedCrossEntropyLoss(weight=w, ignore_index=255).to(DEV)
     x = torch.randn(2, C, 64, 64, device=DEV)
-    t = torch.randint(0, C, (2, 64, 64), device=DEV, dtype=torch.uint8)
+    t = torch.randint(0, C, (2, 64, 64), device=DEV, dtype=torch.int64)
     t[0, :5] = 255
     xa = x.clone().requires_grad_(True)
     la = crit(xa, t)
     la.backward()
     xb = x.clone().requires_grad_(True)
     crit.prefetch_total_weight(t, C)
+    assert crit._prefetched is not None
     lb = crit(xb, t)
     lb.backward()
     assert crit._prefetched is None
     assert la.item() == lb.item() and torch.equal(xa.grad, xb.grad)
+    ref = torch_path.make_criterion(w, 255)
+
+    def check(xc, lc, tt):
+        xr = x.detach().cpu().requires_grad_(True)
+        lr = ref(xr, tt.cpu().long())
+        lr.backward()
+        assert abs(lc.item() - lr.item()) <= 1e-5 * abs(lr.item())
+        assert float((xc.grad.cpu() - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
+
     # a different target tensor does not pick up a stale prefetch
     crit.prefetch_total_weight(t, C)
     t2 = t.clone()
@@ -326,12 +337,88 @@ def test_prefetched_total_weight_gives_identical_results():
     xc = x.clone().requires_grad_(True)
     lc = crit(xc, t2)
     lc.backward()
-    ref = torch_path.make_criterion(w, 255)
-    xr = x.detach().cpu().requires_grad_(True)
-    lr = ref(xr, t2.cpu().long())
-    lr.backward()
-    assert abs(lc.item() - lr.item()) <= 1e-5 * abs(lr.item())
-    assert float((xc.grad.cpu() - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
+    check(xc, lc, t2)
+    # the SAME tensor, modified in place between prefetch and forward: the version counter invalidates the prefetch
+    crit.prefetch_total_weight(t, C)
+    t[1, 10:30] = 255
+    t[0, 40:] = 3
+    xd = x.clone().requires_grad_(True)
+    ld = crit(xd, t)
+    ld.backward()
+    check(xd, ld, t)
+    # uint8 labels need no pre-pass launch: prefetching them is a no-op and the results still agree
+    t8 = t.to(torch.uint8)
+    crit.prefetch_total_weight(t8, C)
+    assert crit._prefetched is None
+    xe = x.clone().requires_grad_(True)
+    le = crit(xe, t8)
+    le.backward()
+    check(xe, le, t)
+
+
+def test_module_edge_cases_from_the_review():
+    from cvcs_b200.loss import FusedCrossEntropyLoss
+    from cvcs_b200.metrics import MulticlassConfusionMatrix
+    torch.manual_seed(5)
+    C = 5
+    x = torch.randn(2, C, 32, 32, device=DEV)
+    t = torch.randint(0, C, (2, 32, 32), device=DEV, dtype=torch.uint8)
+    # (1) a second backward through the same loss is refused with a message that says why
+    xa = x.clone().requires_grad_(True)
+    loss = FusedCrossEntropyLoss()(xa, t)
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second backward"):
+        loss.backward()
+    # (2) the registered weight buffer is what the kernel uses, also after it was replaced / edited
+    crit = FusedCrossEntropyLoss(weight=torch.ones(C)).to(DEV)
+    l1 = crit(x, t).item()
+    new_w = torch.tensor([0.1, 2.0, 0.5, 1.5, 3.0])
+    crit.load_state_dict({"weight": new_w})
+    l2 = crit(x, t).item()
+    l_ref = torch_path.make_criterion(new_w, -100)(x.cpu(), t.cpu().long()).item()
+    assert l1 != l2 and abs(l2 - l_ref) <= 1e-5 * abs(l_ref)
+    with torch.no_grad():
+        crit.weight[0] = 5.0
+    new_w[0] = 5.0
+    l3 = crit(x, t).item()
+    l_ref = torch_path.make_criterion(new_w, -100)(x.cpu(), t.cpu().long()).item()
+    assert abs(l3 - l_ref) <= 1e-5 * abs(l_ref)
+    # (3) a metric whose ignore_index differs from the criterion's would silently count other pixels: refused
+    cm0 = MulticlassConfusionMatrix(num_classes=C, ignore_index=0)
+    with pytest.raises(RuntimeError, match="ignore_index"):
+        FusedCrossEntropyLoss(ignore_index=-100, confusion=cm0)(x, t)
+    cm1 = MulticlassConfusionMatrix(num_classes=C, ignore_index=0)
+    FusedCrossEntropyLoss(ignore_index=0, confusion=cm1)(x, t)           # same filter: fine
+    ref = torch_path.RestatedConfusionMatrix(C, None, 0)
+    ref.update(x.argmax(1).cpu().reshape(1, -1), t.cpu().long().reshape(1, -1))
+    assert torch.equal(cm1.compute(), ref.compute())
+    # (4) out-of-range labels seen by the fused pass reach the metric's validate_args status
+    tb = t.clone()
+    tb[0, 0, :3] = C + 2
+    cm2 = MulticlassConfusionMatrix(num_classes=C)
+    FusedCrossEntropyLoss(confusion=cm2)(x, tb)
+    with pytest.raises(RuntimeError, match="outside"):
+        cm2.compute()
+
+
+def test_functional_wrappers_check_what_crosses_the_abi():
+    from cvcs_b200 import ops
+    x = torch.randn(1, 5, 16, 16, device=DEV)
+    t = torch.randint(0, 5, (1, 16, 16), device=DEV, dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="weight"):
+        ops.ce_fused(x, t, torch.ones(5, dtype=torch.float64, device=DEV), want_grad=False)
+    with pytest.raises(RuntimeError, match="weight"):
+        ops.ce_fused(x, t, torch.ones(4, device=DEV), want_grad=False)
+    with pytest.raises(RuntimeError, match="confmat"):
+        ops.ce_fused(x, t, want_grad=False, confmat=torch.zeros((4, 4), dtype=torch.int64, device=DEV))
+    with pytest.raises(RuntimeError, match="confmat"):
+        ops.ce_fused(x, t, want_grad=False, confmat=torch.zeros((5, 5), dtype=torch.int32, device=DEV))
+    with pytest.raises(RuntimeError, match="argmax"):
+        ops.ce_fused(x, t, want_grad=False, argmax=torch.zeros((1, 16, 8), dtype=torch.uint8, device=DEV))
+    with pytest.raises(RuntimeError, match="dlogits"):
+        ops.ce_fused(x, t, dlogits=torch.empty_like(x).contiguous(memory_format=torch.channels_last), inv_total_weight=1.0)
+    with pytest.raises(RuntimeError, match="loss_sums"):
+        ops.ce_fused(x, t, want_grad=False, loss_sums=torch.zeros(3, device=DEV))
 
 
 def test_c_abi_from_a_plain_c_host(tmp_path):

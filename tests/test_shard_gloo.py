@@ -121,3 +121,50 @@ def test_ownership_policies_balance():
     t = torch.ones(3, dtype=torch.float32)
     with pytest.raises(TypeError):
         shard.all_reduce_sum_(t)
+
+
+def _metric_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pickle
+        from cvcs_b200 import metrics, shard
+        # each rank's share of the tiles -> its own confusion matrix (oracle), restored into a metric object the way a
+        # checkpoint restores it (host state), then ONE sync() per rank
+        tiles = shard.local_tiles(N_SCENES, [H, W], P, rank, world, "round_robin")
+        _, cm, _, _ = _partials(tiles, None)
+        m = metrics.MulticlassConfusionMatrix(num_classes=C, ignore_index=None)
+        m = pickle.loads(pickle.dumps(m))
+        m._s["host"] = torch.from_numpy(cm.copy())
+        before = m.compute().clone()
+        m.sync()                                   # collective: every rank, exactly once
+        q.put((rank, before.numpy(), m.compute().numpy(), m.view("true").compute().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_metric_sync_is_a_collective_over_disjoint_shards():
+    """MulticlassConfusionMatrix.sync(): the sum of the ranks' matrices (each rank evaluated its own tiles) equals the
+    single-process matrix; eval_model does NOT call it unless asked (sync_ranks=False by default: an unsharded loader
+    evaluated on every rank would otherwise be counted world_size times, and a rank-0-only validate() would hang)."""
+    import inspect
+    from cvcs_b200 import metrics, shard
+    assert inspect.signature(metrics.eval_model).parameters["sync_ranks"].default is False
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_metric_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    all_tiles = shard.local_tiles(N_SCENES, [H, W], P, 0, 1, "round_robin")
+    _, cm_single, _, _ = _partials(all_tiles, None)
+    assert np.array_equal(out[0][1] + out[1][1], cm_single)          # the shards were disjoint and complete
+    for _, _, synced, normed in out:
+        assert np.array_equal(synced, cm_single)
+        ref = cm_single / np.maximum(cm_single.sum(1, keepdims=True), 1)
+        assert np.allclose(normed, ref.astype(np.float32))
