@@ -48,6 +48,8 @@ WORKLOADS = {
                  desc="1xB200: fused softmax-CE fwd+bwd + argmax + confusion matrix, batch 16 of 1024x1024, 7 classes, fp32 logits"),
     "cfg3": dict(kind="ce", B=16, C=7, H=1024, W=1024, dtype="bf16", weighted=True, ignore_index=255,
                  desc="same path with bf16 logits, class weights and ignore_index=255 (LoveDA-style labels)"),
+    "bf16c7": dict(kind="ce", B=16, C=7, H=1024, W=1024, dtype="bf16", weighted=False, ignore_index=-100,
+                   desc="cfg2 with bf16 logits (no class weights, nothing ignored: K1 alone, no pre-pass)"),
     "cfg5head": dict(kind="ce", B=16, C=20, H=1024, W=1024, dtype="f32", weighted=False, ignore_index=-100,
                      desc="20-class head alone, fp32 logits, batch 16 per GPU"),
     "c16": dict(kind="ce", B=16, C=16, H=1024, W=1024, dtype="f32", weighted=False, ignore_index=-100,
@@ -170,7 +172,7 @@ def blocky_labels(torch, shape, C, g, dev, block=32):
     return t.contiguous()
 
 
-def synth_inputs(torch, wl, dev, seed, n_sets, label_dtype="u8", layout="nchw"):
+def synth_inputs(torch, wl, dev, seed, n_sets, label_dtype="u8", layout="nchw", block=32):
     """Seeded synthetic logits (randn*3) and blocky labels; cfg3 adds 10% ignore pixels and histogram-derived class
     weights; ignore_index 0 (the reference's ignore_background) simply makes class 0 the ignored one."""
     B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
@@ -179,7 +181,7 @@ def synth_inputs(torch, wl, dev, seed, n_sets, label_dtype="u8", layout="nchw"):
     sets = []
     for _ in range(n_sets):
         x = (torch.randn(B, C, H, W, generator=g, device=dev, dtype=torch.float32) * 3).to(dt)
-        t = blocky_labels(torch, (B, H, W), C, g, dev)
+        t = blocky_labels(torch, (B, H, W), C, g, dev, block=block)
         if wl["ignore_index"] == 255:
             t[torch.rand(B, H, W, generator=g, device=dev) < 0.1] = 255
         if label_dtype == "i64":
@@ -331,14 +333,14 @@ class Ctx:
             self._xchg = shard.WeightExchange(device=self.dev)
         return self._xchg.handle_for(self.dev)
 
-    def set_k1_options(self, path="auto", stages=0, no_wait_hint=False, vecp=0, ctas=0, pdl=0, reserve=0):
+    def set_k1_options(self, path="auto", stages=0, no_wait_hint=False, vecp=0, ctas=0, pdl=1, reserve=0):
         L = self.lib
         L.set_option(L.OPT_CE_PATH, {"auto": 0, "tma": 1, "direct": 2, "generic": 3}[path])
         L.set_option(L.OPT_TMA_STAGES, stages)
         L.set_option(L.OPT_TMA_WAIT_HINT, 1 if no_wait_hint else 0)
         L.set_option(L.OPT_TMA_VECP, vecp)
         L.set_option(L.OPT_TMA_CTAS, ctas)
-        L.set_option(L.OPT_PDL, pdl)
+        L.set_option(L.OPT_PDL, 1 if pdl else 2)
         L.set_option(L.OPT_RESERVE_SMS, reserve)
 
 
@@ -353,11 +355,14 @@ def roofline_dict(ctx, achieved_gbs, bpp, px, k_ms, kernel, traffic_key, source,
 
 
 def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, label_dtype=None, layout="nchw",
-               per_launch_events=True, copy_ref=False, want_clocks=True, tw_mode="kernel"):
-    """K1 on rotating buffer sets larger than L2.  When Σ v·w[y] is data dependent (class weights / ignore_index) it is
-    computed by K1 itself (tw_mode "kernel": label pre-pass + grid barrier inside the launch, and at N > 1 the ranks'
-    sums exchanged inside the kernel over NVLink) or, for int64 labels and with tw_mode "chain", by a K4 launch one
-    step ahead on a side stream (at N > 1 followed by an NCCL all-reduce).  Returns a result dict."""
+               per_launch_events=True, copy_ref=False, want_clocks=True, tw_mode="auto", label_block=32):
+    """K1 on rotating buffer sets larger than L2.  When Σ v·w[y] is data dependent (class weights / ignore_index):
+      tw_mode "chain"   a K4 launch one step ahead on a side stream (the next batch's labels are known while the current
+                        K1 runs); at N > 1 followed by an NCCL all-reduce of the 8-byte sum
+      tw_mode "xchg"    the same K4, but the ranks' sums are exchanged INSIDE K1 over NVLink peer memory (no NCCL)
+      tw_mode "kernel"  no K4 at all: K1 sums the weights in its own label pre-pass (grid barrier), then exchanges
+      tw_mode "auto"    "chain" on one GPU, "xchg" on several
+    Returns a result dict."""
     torch, dist, ops, dev, world = ctx.torch, ctx.dist, ctx.ops, ctx.dev, ctx.world
     label_dtype = label_dtype or wl.get("label_dtype", "u8")
     B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
@@ -366,16 +371,21 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
     grad = grad and not metrics_only
     set_bytes = px_per_gpu * C * esize * (2 if grad else 1)
     n_sets = max(3, min(16, -(-400_000_000 // set_bytes)))     # rotate >= 400 MB (L2 is 126 MB) through the caches
-    sets, weight = synth_inputs(torch, wl, dev, seed=1234 + ctx.rank, n_sets=n_sets, label_dtype=label_dtype, layout=layout)
+    sets, weight = synth_inputs(torch, wl, dev, seed=1234 + ctx.rank, n_sets=n_sets, label_dtype=label_dtype, layout=layout,
+                                block=label_block)
     dl = [torch.empty_like(x) for x, _ in sets] if grad else [None] * n_sets
     am = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in sets]
     confmat = torch.zeros((C, C), dtype=torch.int64, device=dev)
     loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
     ii = wl["ignore_index"]
     data_dependent_tw = wl["weighted"] or (0 <= ii <= 255) or label_dtype == "i64"
+    if tw_mode == "auto":
+        tw_mode = "xchg" if world > 1 else "chain"
     tw_kernel = grad and data_dependent_tw and tw_mode == "kernel" and label_dtype == "u8"
     prepass_on = grad and data_dependent_tw and not tw_kernel
-    xchg = ctx.exchange() if (tw_kernel and world > 1) else None
+    tw_xchg = prepass_on and tw_mode in ("xchg", "kernel") and world > 1      # K4 locally, exchange inside K1
+    xchg = ctx.exchange() if ((tw_kernel or tw_xchg) and world > 1) else None
+    twg = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(n_sets)] if tw_xchg else None
     # K4 pre-pass (Σ v·w[y] must be known before the first dlogit is written) runs ONE STEP AHEAD on its own
     # stream: the labels of the next batch are known while the current K1 runs (as in a training loop with a
     # prefetching loader), so the pre-pass — and at N > 1 its all-reduce — overlaps K1.
@@ -400,7 +410,7 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
         if k1_done[j] is not None:
             pre.wait_event(k1_done[j])
         with torch.cuda.stream(pre):
-            if world > 1:
+            if world > 1 and not tw_xchg:
                 ops.label_hist(t, C, ii, weight=weight, total_weight_out=tws[j])    # this rank's Σ v·w[y] (fp64)
                 dist.all_reduce(tw_sum[j])                      # global Σw: every rank divides by the same total
                 torch.reciprocal(tw_sum[j], out=tw_inv[j])
@@ -434,13 +444,17 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         t_k1, ii_k1 = t, ii
-        if prepass_on and world == 1 and t.dtype == torch.int64:
+        if prepass_on and (world == 1 or tw_xchg) and t.dtype == torch.int64:
             t_k1, ii_k1 = t8s[j], 255                         # byte labels written by cvcs_labels_prepare
         if metrics_only:
             ops.eval_fused(x, t, ii, argmax=am[j], confmat=confmat)
         elif tw_kernel:
             ops.ce_fused(x, t, weight, ii, want_grad=True, total_weight="kernel", xchg=xchg, total_weight_out=tws[j],
                          dlogits=dl[j], argmax=am[j], confmat=confmat, loss_sums=sums_table[i % sums_rows], loss_out=loss_out)
+        elif tw_xchg:
+            ops.ce_fused(x, t_k1, weight, ii_k1, want_grad=True, total_weight="kernel", xchg=xchg, local_total_weight=tw_sum[j],
+                         total_weight_out=twg[j], dlogits=dl[j], argmax=am[j], confmat=confmat,
+                         loss_sums=sums_table[i % sums_rows], loss_out=loss_out)
         else:
             ops.ce_fused(x, t_k1, weight, ii_k1, want_grad=grad, inv_total_weight=inv, inv_total_weight_dev=inv_dev,
                          dlogits=dl[j], argmax=am[j], confmat=confmat, loss_sums=sums_table[i % sums_rows], loss_out=loss_out)
@@ -520,11 +534,13 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
                                   {"same_size_copy_gbs_in_this_harness": copy_gbs}),
         "gpu_launches": launches["n"], "host_enqueue_ms_per_step": host_ms, "per_rank": per_rank,
         "check": {"confusion_total": int(confmat.sum().item()), "loss": float(loss_out.item())},
-        "config": {"per_gpu_batch": B, "classes": C, "tile": [H, W], "labels": label_dtype + " (blocky 32x32)", "grad": grad,
+        "config": {"per_gpu_batch": B, "classes": C, "tile": [H, W],
+                   "labels": label_dtype + (f" (blocky {label_block}x{label_block})" if label_block > 1 else " (i.i.d.)"), "grad": grad,
                    "metrics_only": metrics_only, "layout": layout,
                    "l2": f"inputs larger than L2: {n_sets} rotating sets of {set_bytes / 1e6:.0f} MB",
                    "total_weight": ("computed inside K1 (label pre-pass + grid barrier" + (", exchanged across ranks over NVLink inside the kernel)" if xchg is not None else ")"))
-                   if tw_kernel else ("K4 pre-pass one step ahead on a side stream" + (" + NCCL all-reduce" if world > 1 else "")
+                   if tw_kernel else (("K4 pre-pass one step ahead on a side stream" + (", the ranks' sums exchanged inside K1 over NVLink peer memory" if tw_xchg
+                                                                                        else (" + NCCL all-reduce" if world > 1 else "")))
                                       if prepass_on else "constant (nothing can be ignored)")},
         "_state": (sets, weight),
     }
@@ -805,18 +821,18 @@ def run_secondary(ctx, names, steps, warmup):
                 wl = dict(WORKLOADS[nm])
                 kind = wl["kind"]
                 if kind == "ce":
-                    r = measure_ce(ctx, nm, wl, steps, warmup, want_clocks=False)
+                    r = measure_ce(ctx, nm, wl, steps, warmup, want_clocks=False, per_launch_events=False)
                 elif kind == "chain":
                     st = max(4, min(steps, 12)) if nm == "cfg5" else steps
                     r = measure_chain(ctx, nm, wl, st, min(warmup, 3), want_clocks=False)
                 else:
                     r = measure_tile(ctx, nm, wl, min(steps, 20), min(warmup, 3), want_clocks=False)
             elif nm == "eval_only":
-                r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, grad=False, want_clocks=False)
+                r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, grad=False, want_clocks=False, per_launch_events=False)
             elif nm == "metrics_only":
-                r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, metrics_only=True, want_clocks=False)
+                r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, metrics_only=True, want_clocks=False, per_launch_events=False)
             elif nm == "i64_labels":
-                r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, label_dtype="i64", want_clocks=False)
+                r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, label_dtype="i64", want_clocks=False, per_launch_events=False)
             else:
                 continue
             rf = r["roofline"]
@@ -854,11 +870,13 @@ def main():
     ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"], help="logits memory format (nhwc = torch channels_last)")
     ap.add_argument("--no-grad", action="store_true", help="forward/eval only (no dlogits)")
     ap.add_argument("--metrics-only", action="store_true", help="K1 metrics mode: argmax + confusion matrix, no loss (cvcs_eval_fused)")
-    ap.add_argument("--pdl", type=int, default=0, choices=[0, 1],
-                    help="1: K1 launches with programmatic stream serialization (prologue overlaps the previous kernel's tail); "
-                         "per-launch events would serialise the launches, so K1's average launch time is then region / steps")
-    ap.add_argument("--tw-mode", default="kernel", choices=["kernel", "chain"],
-                    help="data dependent total weight: computed inside K1 (default) or by a K4 launch (+ NCCL all-reduce at N > 1)")
+    ap.add_argument("--pdl", type=int, default=1, choices=[0, 1],
+                    help="1 (default, the library's default): K1 launches with programmatic stream serialization (its prologue overlaps "
+                         "the previous kernel's tail); per-launch events would serialise the launches, so K1's average launch time "
+                         "is then timed region / steps.  0: plain launches with CUDA events around every one")
+    ap.add_argument("--label-block", type=int, default=32, help="side of the constant label blocks (1 = i.i.d. labels)")
+    ap.add_argument("--tw-mode", default="auto", choices=["auto", "kernel", "chain", "xchg"],
+                    help="data dependent total weight (see measure_ce): auto = chain on one GPU, xchg on several")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-copy-ref", action="store_true", help="skip the same-size torch copy reference measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -884,8 +902,7 @@ def main():
     label_dtype = args.label_dtype or wl.get("label_dtype", "u8")
     data_dependent_tw = kind == "ce" and grad and (wl["weighted"] or (0 <= wl["ignore_index"] <= 255) or label_dtype == "i64")
     # a per-step collective (global Σw) has to run WHILE K1 runs: leave it two SMs (K1 claims chunks dynamically)
-    reserve = args.reserve_sms if args.reserve_sms >= 0 else (
-        2 if (world > 1 and data_dependent_tw and (args.tw_mode == "chain" or label_dtype != "u8")) else 0)
+    reserve = args.reserve_sms if args.reserve_sms >= 0 else (2 if (world > 1 and data_dependent_tw and args.tw_mode == "chain") else 0)
     opts = dict(path=args.path, stages=args.stages, no_wait_hint=args.no_wait_hint, vecp=args.vecp, ctas=args.ctas,
                 pdl=args.pdl, reserve=reserve)
     ctx.set_k1_options(**opts)
@@ -894,11 +911,11 @@ def main():
         ctx.lib.set_option(ctx.lib.OPT_TMA_CTAS, 0)
         res = measure_tile(ctx, args.workload, wl, args.steps, args.warmup)
     elif kind == "chain":
-        res = measure_chain(ctx, args.workload, wl, args.steps, args.warmup, per_launch_events=not args.pdl)
+        res = measure_chain(ctx, args.workload, wl, args.steps, args.warmup)
     else:
         res = measure_ce(ctx, args.workload, wl, args.steps, args.warmup, grad=grad, metrics_only=args.metrics_only,
                          label_dtype=label_dtype, layout=args.layout, per_launch_events=not args.pdl,
-                         copy_ref=not args.no_copy_ref, tw_mode=args.tw_mode)
+                         copy_ref=not args.no_copy_ref, tw_mode=args.tw_mode, label_block=args.label_block)
     clocks = ctx.sampler.summary()
 
     e2e = e2e_eval = tcb = cpu = None

@@ -53,7 +53,7 @@ SIGNATURES = {
     "cvcs_labels_prepare": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _vp, _vp, _vp]),
     "cvcs_ce_fused": (_i, [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _vp,
                            _vp, _vp, _vp]),
-    "cvcs_ce_fused_tw": (_i, [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp,
+    "cvcs_ce_fused_tw": (_i, [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp,
                               _vp, _vp, _vp]),
     "cvcs_xchg_create": (_i, [C.POINTER(_vp), _i, _i]),
     "cvcs_xchg_local_handle": (_i, [_vp, _vp]),
@@ -69,6 +69,7 @@ SIGNATURES = {
     "cvcs_confmat": (_i, [_vp, _i, _vp, _i, _ll, _i, _ll, _vp, _vp, _vp, _vp]),
     "cvcs_tile_normalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _ll,
                                  _vp, _vp]),
+    "cvcs_tile_context": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "cvcs_vote": (_i, [_vp, _i, _i, _ll, _i, _vp, _i, _vp]),
     "cvcs_colorize": (_i, [_vp, _i, _ll, _vp, _i, _vp, _vp]),
     "cvcs_stitch": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),

@@ -50,6 +50,7 @@ int confmat_launch(const void*, int, const void*, int, long long, int, long long
 int tile_launch(const unsigned char*, int, int, int, const int*, const int*, int, int, int, const float*, const float*, void*, int,
                 const unsigned char*, void*, int, unsigned long long*, int, long long, void*, cudaStream_t);
 int stitch_launch(const unsigned char*, int, int, int, const int*, int, int, unsigned char*, int, int, cudaStream_t);
+int context_launch(const unsigned char*, int, int, int, const int*, const int*, int, int, unsigned char*, cudaStream_t);
 int vote_launch(const void*, int, int, long long, int, void*, int, cudaStream_t);
 int colorize_launch(const void*, int, long long, const float*, int, float*, cudaStream_t);
 
@@ -235,10 +236,11 @@ int cvcs_xchg_destroy(cvcs_xchg* x) {
 
 int cvcs_ce_fused_tw(const void* logits_dev, int logits_dtype, int layout, const void* target_dev, int target_dtype,
                      const float* weight_dev, long long ignore_index, int B, int C, int H, int W, cvcs_xchg* xchg,
-                     double* total_weight_out_dev, void* dlogits_dev, void* argmax_dev, int argmax_dtype,
+                     const double* local_total_weight_dev, double* total_weight_out_dev, void* dlogits_dev, void* argmax_dev, int argmax_dtype,
                      unsigned long long* confmat_dev, double* loss_sums_dev, float* loss_out_dev, void* workspace_dev,
                      void* stream) {
     TwRequest tw{};
+    tw.tw_local = local_total_weight_dev;
     tw.tw_out = total_weight_out_dev;
     tw.world = 1;
     tw.rank = 0;
@@ -290,6 +292,11 @@ int cvcs_tile_normalize(const unsigned char* scene_dev, int Cb, int H, int W, co
     return tile_launch(scene_dev, Cb, H, W, tile_yx_dev, tile_slot_dev, n_tiles, tile_h, tile_w, mean_dev, std_dev, out_dev, out_dtype,
                        label_dev, label_out_dev, label_out_dtype, hist_dev, hist_C, hist_ignore_index, workspace_dev,
                        static_cast<cudaStream_t>(stream));
+}
+
+int cvcs_tile_context(const unsigned char* scene_dev, int Cb, int H, int W, const int* tile_yx_dev, const int* tile_slot_dev,
+                      int n_tiles, int p, unsigned char* out_dev, void* stream) {
+    return context_launch(scene_dev, Cb, H, W, tile_yx_dev, tile_slot_dev, n_tiles, p, out_dev, static_cast<cudaStream_t>(stream));
 }
 
 int cvcs_vote(const void* maps_dev, int dtype, int n_maps, long long n_pixels, int C, void* out_dev, int out_dtype,

@@ -34,7 +34,9 @@ struct CeParams {
     int no_loss;     // 1: metrics mode — argmax + confusion matrix only, no softmax / loss (loss_sums may be NULL)
     // total weight computed by the kernel itself (TMA variant): a label pre-pass by every CTA, a grid-wide barrier
     // and — across GPUs — a one-shot exchange over peer-mapped memory, all before the first gradient is written
-    int tw_mode;                 // 0: inv_tw / inv_tw_dev above; 1: in-kernel pre-pass
+    int tw_mode;                 // 0: inv_tw / inv_tw_dev above; 1: in-kernel label pre-pass (+ exchange);
+                                 // 2: this rank's Σ given in tw_local_dev (a K4 launch), exchange in the kernel
+    const double* tw_local_dev;  // tw_mode 2: f64[1]
     double* tw_out;              // nullable f64[2]: {Σ v·w[y] (global), 1/Σ}
     int xworld, xrank;           // ranks taking part in the exchange (1 = this GPU only)
     XchgBlock* xpeer[kXMaxRanks];  // every rank's exchange block (xpeer[xrank] is the local one)
@@ -42,6 +44,7 @@ struct CeParams {
 
 // what cvcs_ce_fused_tw asks of the launcher: compute the total weight in the kernel, optionally exchanged across ranks
 struct TwRequest {
+    const double* tw_local;        // nullable: this rank's Σ v·w[y] already on the device (skips the label pre-pass)
     double* tw_out;                // nullable f64[2]
     int world, rank;
     XchgBlock* peer[kXMaxRanks];   // peer[rank] = local block; unused when world == 1
@@ -351,13 +354,15 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
         }
         p.ws->partial[2 * blockIdx.x] = a;
         p.ws->partial[2 * blockIdx.x + 1] = b;
-        __threadfence();
-        const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
+        // one acq_rel ticket instead of fence + atomic + fence: its release publishes this CTA's partials (and, through
+        // the barrier above, its warps' out-of-bounds counts), its acquire — in the CTA that draws the last ticket —
+        // makes every earlier CTA's visible to the fold below (the barrier after it extends that to the other threads)
+        unsigned int t;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(&p.ws->ticket) : "memory");
         is_last = (t == gridDim.x - 1);
     }
     sync();
     if (!is_last) return;
-    __threadfence();
     const unsigned long long nbad = __ldcg(&p.ws->bad);   // every CTA's count landed before its ticket
     double a = 0.0, b = 0.0;
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += NWARPS * 32) {
@@ -395,7 +400,7 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
         p.ws->ticket = 0u;
         p.ws->next_chunk = 0u;
         p.ws->gbar = 0u;
-        if (p.tw_mode == 1 && p.xworld > 1) p.xpeer[p.xrank]->seq += 1ull;   // every CTA read it long ago (grid barrier)
+        if (p.tw_mode != 0 && p.xworld > 1) p.xpeer[p.xrank]->seq += 1ull;   // every CTA read it in its prologue, long ago
         __threadfence();
     }
 }

@@ -16,6 +16,7 @@ int ce_tma_launch_bf16(const CeParams& p, int layout, cudaStream_t stream, bool*
 
 int label_hist_launch(const void*, int, long long, int, long long, unsigned long long*, const float*, double*, void*,
                       cudaStream_t);
+int reciprocal_launch(const double* in, double* out2, cudaStream_t stream);   // out2 = {in[0], 1 / in[0]}
 
 // tw_mode 1 on a shape the TMA-staged kernel does not take (odd sizes, int64 labels, C > 21, a forced variant): the
 // same result from two launches — K4 (lean: Σ v·w[y] only) into tw_out, then K1 reading 1/Σ from there.  Single GPU
@@ -24,8 +25,15 @@ static int tw_fallback(CeParams p, int logits_dtype, int layout, int target_dtyp
     if (p.xworld > 1)
         return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_ce_fused_tw: the cross-GPU exchange needs a shape the TMA-staged kernel takes "
                          "(u8 labels, 16-byte aligned tensors, H*W %% 16 == 0, 2 <= C <= %d)", kMaxRegC);
-    CVCS_REQUIRE(p.tw_out, "cvcs_ce_fused_tw: total_weight_out_dev is needed for this shape (two-launch fallback)");
-    int rc = label_hist_launch(p.target, target_dtype, p.n_pixels, p.C, p.ignore_index, nullptr, p.weight, p.tw_out, p.ws, stream);
+    int rc = CVCS_OK;
+    if (p.tw_mode == 2) {
+        // Σ already on the device: only its reciprocal is missing
+        CVCS_REQUIRE(p.tw_out, "cvcs_ce_fused_tw: total_weight_out_dev is needed for this shape (fallback path)");
+        rc = reciprocal_launch(p.tw_local_dev, p.tw_out, stream);
+    } else {
+        CVCS_REQUIRE(p.tw_out, "cvcs_ce_fused_tw: total_weight_out_dev is needed for this shape (two-launch fallback)");
+        rc = label_hist_launch(p.target, target_dtype, p.n_pixels, p.C, p.ignore_index, nullptr, p.weight, p.tw_out, p.ws, stream);
+    }
     if (rc) return rc;
     p.tw_mode = 0;
     p.inv_tw_dev = p.tw_out + 1;
@@ -99,7 +107,8 @@ int ce_fused_launch(const void* logits, int logits_dtype, int layout, const void
         // total weight computed by K1 itself (label pre-pass + grid barrier [+ exchange]); forward-only calls do not need it
         CVCS_REQUIRE(tw->world >= 1 && tw->world <= kXMaxRanks && tw->rank >= 0 && tw->rank < tw->world,
                      "cvcs_ce_fused_tw: bad exchange geometry (world %d, rank %d)", tw->world, tw->rank);
-        p.tw_mode = 1;
+        p.tw_mode = tw->tw_local ? 2 : 1;
+        p.tw_local_dev = tw->tw_local;
         p.tw_out = tw->tw_out;
         p.xworld = tw->world;
         p.xrank = tw->rank;
@@ -115,17 +124,17 @@ int ce_fused_launch(const void* logits, int logits_dtype, int layout, const void
     bool handled = false;
     int rc = CVCS_OK;
 
-    if (p.tw_mode == 1 && !(forced != 3 && C >= 2 && C <= kMaxRegC && ptr16)) return tw_fallback(p, logits_dtype, layout, target_dtype, stream);
+    if (p.tw_mode != 0 && !(forced != 3 && C >= 2 && C <= kMaxRegC && ptr16)) return tw_fallback(p, logits_dtype, layout, target_dtype, stream);
     if (forced != 3 && C >= 2 && C <= kMaxRegC && ptr16) {
         // ---- TMA-staged: every bulk copy must be a multiple of 16 bytes
         const bool tma_ok = layout == CVCS_NCHW ? (hw % 16 == 0) : (n_pixels % 16 == 0);
-        if (p.tw_mode == 1 && !(tma_ok && forced != 2 && forced != 3 && target_dtype == CVCS_U8))
+        if (p.tw_mode != 0 && !(tma_ok && forced != 2 && forced != 3 && (target_dtype == CVCS_U8 || p.tw_mode == 2)))
             return tw_fallback(p, logits_dtype, layout, target_dtype, stream);
         if (tma_ok && forced != 2) {
             rc = logits_dtype == CVCS_F32 ? ce_tma_launch_f32(p, layout, stream, &handled)
                                           : ce_tma_launch_bf16(p, layout, stream, &handled);
             if (handled) return rc;
-            if (p.tw_mode == 1) return tw_fallback(p, logits_dtype, layout, target_dtype, stream);
+            if (p.tw_mode != 0) return tw_fallback(p, logits_dtype, layout, target_dtype, stream);
         }
         // ---- direct NCHW: f32 4 pixels/thread; bf16 8 pixels/thread up to C=12, else 4
         if (layout == CVCS_NCHW && forced != 1) {

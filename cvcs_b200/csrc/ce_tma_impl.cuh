@@ -231,6 +231,32 @@ __device__ __forceinline__ double prepass_total_weight(const CeParams& p, int ti
     return total;
 }
 
+// tw_mode 2: this rank's Σ v·w[y] comes from a K4 launch (e.g. one step ahead on a side stream); only the cross-GPU
+// exchange happens here, in the shadow of the pipeline fill.  Called by threads 0..kThreads-1.
+__device__ __forceinline__ double exchanged_total_weight(const CeParams& p, int tid) {
+    __shared__ double total;
+    if (tid == 0) {
+        double v = __ldcg(p.tw_local_dev);
+        if (p.xworld > 1) v = xchg_total_weight(p, v, blockIdx.x == 0);
+        total = v;
+        if (blockIdx.x == 0 && p.tw_out) {
+            p.tw_out[0] = v;
+            p.tw_out[1] = 1.0 / v;
+        }
+    }
+    asm volatile("bar.sync %0, %1;" ::"n"(kConsumerBar), "n"(kThreads) : "memory");
+    return total;
+}
+
+template <int SUB>
+struct HistCounter {
+    using type = unsigned short;
+};
+template <>
+struct HistCounter<2> {
+    using type = unsigned char;
+};
+
 // SUB: sub-chunks of kThreads*VECP pixels per stage.  A consumer thread handles VECP consecutive pixels of every
 // sub-chunk, so SUB > 1 doubles the bytes per bulk copy and halves the per-stage bookkeeping per pixel without
 // widening the thread's register working set.
@@ -370,11 +396,15 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
         if (tid < C) wsm[tid] = p.weight ? p.weight[tid] : 1.0f;
         float inv_tw = do_grad ? static_cast<float>(p.inv_tw_dev ? __ldcg(p.inv_tw_dev) : p.inv_tw) : 0.f;
         if constexpr (do_grad) {
-            if (p.tw_mode == 1) inv_tw = static_cast<float>(1.0 / prepass_total_weight<C>(p, tid));   // grid-wide; see below
+            if (p.tw_mode == 1) inv_tw = static_cast<float>(1.0 / prepass_total_weight<C>(p, tid));   // grid-wide; see above
+            else if (p.tw_mode == 2) inv_tw = static_cast<float>(1.0 / exchanged_total_weight(p, tid));
         }
-        BinAcc<PRIV, kConsumerBar> conf;
+        // private counters: 16-bit, or 8-bit when a stage holds several sub-chunks (half the shared memory, which buys a
+        // third stage for two CTAs per SM; a CTA of a 16-tile bf16 batch never reaches 255 pixels per thread anyway)
+        using Conf = BinAcc<PRIV, kConsumerBar, typename HistCounter<SUB>::type>;
+        Conf conf;
         if (do_conf) conf.init(smem + g.hist_off, C * C);
-        else BinAcc<PRIV, kConsumerBar>::sync();      // wsm visible to all consumers
+        else Conf::sync();      // wsm visible to all consumers
         const int ign8 = ignore_as_int_u8(p.ignore_index);
         // byte-parallel label classification constants (u8 labels, C <= 128): see classify_labels_u8x4
         const uint32_t lab_ge_add = static_cast<uint32_t>(128 - C) * 0x01010101u;
@@ -633,21 +663,10 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                         for (int k = 0; k < VECP; ++k)
                             if (valid[k]) conf.add(tcl[k] * C + amax[k]);
                     } else {
-                        // shared bins (C*C > 64): equal (target, prediction) pairs of the thread's consecutive pixels are
-                        // merged first (masks and predictions have runs), then equal pairs across the warp
-                        int key[VECP];
+                        // shared bins (C*C > 64): one shared-memory atomic per pixel on this warp's replica
 #pragma unroll
-                        for (int k = 0; k < VECP; ++k) key[k] = valid[k] ? tcl[k] * C + amax[k] : -1;
-                        unsigned int run = 0;
-#pragma unroll
-                        for (int k = 0; k < VECP; ++k) {
-                            ++run;
-                            const bool last = (k == VECP - 1) || key[k + 1 < VECP ? k + 1 : k] != key[k];
-                            if (last) {
-                                if (key[k] >= 0) conf.add_agg(key[k], run);
-                                run = 0;
-                            }
-                        }
+                        for (int k = 0; k < VECP; ++k)
+                            if (valid[k]) conf.add(tcl[k] * C + amax[k]);
                     }
                 }
                 // ---- registers -> shared (in place), then the target-class entries
@@ -680,7 +699,7 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
             if constexpr (do_grad) fence_async_smem();  // make the in-place gradients visible to the bulk store
             mbar_arrive(full_bar + 8 * kMaxStages);
             if (PRIV && do_conf) {
-                if (since_flush > 65535u - VECP * SUB) {
+                if (since_flush > Conf::kMaxCount - VECP * SUB) {
                     conf.flush(p.confmat);
                     since_flush = 0;
                 }
@@ -730,14 +749,13 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     g.label_off = C * P * ES;
     g.stage_bytes = ((g.label_off + P * tsize + 127) / 128) * 128;
     g.hist_off = 0;
-    const int hist_bytes = p.confmat ? BinAcc<PRIV>::smem_bytes(C * C) : 0;
+    const int hist_bytes = p.confmat ? BinAcc<PRIV, 0, typename HistCounter<SUB>::type>::smem_bytes(C * C) : 0;
     g.stage_off = ((hist_bytes + 127) / 128) * 128;
-    // Pipeline geometry (measured on B200).  With gradients (read + write streams) the
-    // sustained HBM rate peaks when the stages resident on an SM total ~90-125 KB and falls off on either
-    // side (59 KB: 0.74, 89 KB: 0.90, 119 KB: 0.84, 178 KB: 0.83 of the measured copy peak for fp32 C=7):
-    // 3 stages per CTA, and 2 CTAs per SM only while 2 x 3 stages stay within 128 KB.  Forward-only
-    // (read stream only, issue-bound) wants warps and bytes in flight: 3 CTAs when 3 stages each still
-    // fit (C=20: 0.58 -> 0.72 of peak), else 2 CTAs with as many stages as the budget allows.
+    // Pipeline geometry (measured on B200, profiles/README.md "K1 geometry, round 2").  With gradients the kernel wants
+    // 4 stages per CTA (fp32 C=7, 1 CTA/SM: 3 stages 0.945, 4-6 stages 0.99 of the measured copy peak, 7 stages 0.945;
+    // bf16 C=7, 2 CTAs/SM: 3 stages 0.81, 4-5 stages 0.835) and two CTAs per SM whenever each can still hold 3 stages
+    // (bf16 is issue-limited with 8 consumer warps per SM: 1 CTA 0.59-0.72).  Forward-only kernels (64 registers) run
+    // 3 CTAs per SM when each still holds 3 stages, else 2 (fp32 C=7: 2 CTAs x 3..6 stages all 0.93, 3 CTAs x 2: 0.69).
     const bool grad = p.dlogits != nullptr;
     auto kernel = p.dlogits ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, true, true, SUB>
                             : (p.no_loss ? ce_tma_kernel<T, C, VECP, NHWC, PRIV, false, false, SUB> : ce_tma_kernel<T, C, VECP, NHWC, PRIV, false, true, SUB>);
@@ -754,7 +772,7 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     int target_ctas = get_option(CVCS_OPT_TMA_CTAS);
     const bool ctas_forced = target_ctas >= 1 && target_ctas <= 4;
     if (!ctas_forced) {
-        if (grad) target_ctas = (2 * 3 * g.stage_bytes > 128 * 1024) ? 1 : 2;
+        if (grad) target_ctas = ((233472 / 2 - reserve - g.stage_off) / g.stage_bytes >= 3) ? 2 : 1;
         else target_ctas = ((233472 / 3 - reserve - g.stage_off) / g.stage_bytes >= 3) ? 3 : 2;  // forward-only kernels fit 3 CTAs (64 regs)
     }
     const int per_cta = 233472 / target_ctas - reserve;  // 228 KB per SM
@@ -763,7 +781,7 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
         target_ctas = 1;
         stages = (227 * 1024 - reserve + 1024 - g.stage_off) / g.stage_bytes;
     }
-    if (grad && stages > 3) stages = 3;
+    if (grad && stages > 4) stages = 4;
     if (stages > kMaxStages) stages = kMaxStages;
     const int want_stages = get_option(CVCS_OPT_TMA_STAGES);
     if (want_stages >= 2 && want_stages <= kMaxStages && want_stages <= (per_cta - g.stage_off) / g.stage_bytes) stages = want_stages;
@@ -808,7 +826,7 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         CVCS_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p, g));
-    } else if (get_option(CVCS_OPT_PDL) == 1) {
+    } else if (get_option(CVCS_OPT_PDL) != 2) {
         // programmatic stream serialization: this launch may start while the previous kernel of the stream drains
         // (the kernel itself waits, griddepcontrol.wait, before it reads anything the predecessor wrote)
         cudaLaunchConfig_t cfg{};

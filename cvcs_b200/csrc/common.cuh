@@ -245,14 +245,15 @@ __device__ __forceinline__ bool better(float v, float best) {
 // not fit shared memory at all and every hit is a 64-bit global atomic.  CTAs are kThreads wide.
 // BAR = 0: the accumulator is used by the whole CTA (__syncthreads); BAR > 0: by threads
 // 0..kThreads-1 of a wider CTA, synchronised on named barrier BAR.
-template <bool PRIV, int BAR = 0>
+template <bool PRIV, int BAR = 0, typename CT = unsigned short>
 struct BinAcc {
+    static constexpr unsigned int kMaxCount = sizeof(CT) == 1 ? 255u : 65535u;   // private counter range
     static __device__ __forceinline__ void sync() {
         if constexpr (BAR == 0) __syncthreads();
         else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(kThreads) : "memory");
     }
-    unsigned short* cnt16;
-    unsigned short* mine;      // PRIV: cnt16 + threadIdx.x (this thread's counter of bin 0)
+    CT* cnt16;
+    CT* mine;                  // PRIV: cnt16 + threadIdx.x (this thread's counter of bin 0)
     unsigned int* bins32;
     unsigned long long* direct;
     int nb;
@@ -264,10 +265,10 @@ struct BinAcc {
         reps = replicas;
         direct = global_bins;
         if constexpr (PRIV) {
-            cnt16 = reinterpret_cast<unsigned short*>(smem);
+            cnt16 = reinterpret_cast<CT*>(smem);
             mine = cnt16 + threadIdx.x;
             uint32_t* z = reinterpret_cast<uint32_t*>(smem);
-            for (int i = threadIdx.x; i < nb * kThreads / 2; i += kThreads) z[i] = 0u;
+            for (int i = threadIdx.x; i < nb * kThreads * static_cast<int>(sizeof(CT)) / 4; i += kThreads) z[i] = 0u;
         } else {
             bins32 = reinterpret_cast<unsigned int*>(smem);
             for (int i = threadIdx.x; i < nb * reps; i += kThreads) bins32[i] = 0u;
@@ -276,27 +277,19 @@ struct BinAcc {
     }
     __device__ __forceinline__ void add(int key, unsigned int n = 1u) {
         if constexpr (PRIV) {
-            unsigned short* c = mine + key * kThreads;
-            *c = static_cast<unsigned short>(*c + n);
+            CT* c = mine + key * kThreads;
+            *c = static_cast<CT>(*c + n);
         } else {
             if (reps) atomicAdd(bins32 + ((threadIdx.x >> 5) & (reps - 1)) * nb + key, n);
             else atomicAdd(direct + key, static_cast<unsigned long long>(n));
         }
     }
-    // Shared mode with warp aggregation: the lanes of a warp that hit the SAME bin with the same increment merge into
-    // one shared-memory atomic issued by the lowest such lane (match.any + popc) — blocky label maps put whole warps on
-    // one or two bins, which would otherwise serialise on one address.  Callable from divergent code (the match runs
-    // over the lanes that are converged here).  Private mode: a plain private update.
-    __device__ __forceinline__ void add_agg(int key, unsigned int n = 1u) {
-        if constexpr (PRIV) {
-            add(key, n);
-        } else {
-            const unsigned int peers = __match_any_sync(__activemask(), (key << 4) | static_cast<int>(n & 15u));
-            if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) add(key, n * static_cast<unsigned int>(__popc(peers)));
-        }
-    }
+    // (Round 2 measured warp-aggregated updates for the shared mode — match.any + popc/redux, leaders only, with and
+    // without atomics — on B200: the match instruction costs far more than the same-address atomics it removes (C=16
+    // metrics mode 0.94 -> 0.46 of the copy peak, C=20 0.81 -> 0.74; profiles/README.md), so the plain per-lane
+    // shared-memory atomic on a per-warp replica stays.)
     static __host__ __device__ int smem_bytes(int nbins, int replicas = kWarps) {
-        return PRIV ? nbins * kThreads * 2 : nbins * replicas * 4;
+        return PRIV ? nbins * kThreads * static_cast<int>(sizeof(CT)) : nbins * replicas * 4;
     }
     // CTA-wide flush to global u64 bins; leaves the counters zeroed.
     __device__ __forceinline__ void flush(unsigned long long* confmat) {
@@ -307,7 +300,7 @@ struct BinAcc {
                 unsigned int s = 0;
 #pragma unroll
                 for (int j = 0; j < kThreads / 32; ++j) {
-                    unsigned short* c = cnt16 + b * kThreads + j * 32 + lane;
+                    CT* c = cnt16 + b * kThreads + j * 32 + lane;
                     s += *c;
                     *c = 0;
                 }

@@ -1,0 +1,140 @@
+// context_kernel.cu — N4: the context view of a patch (reference dataset.py:11-16 `_get_context`):
+//     context = Resize(p)( crop(image, tly - p, tlx - p, 3p, 3p) )
+// i.e. the 3p x 3p neighbourhood of the patch (zeros outside the scene, torchvision crop semantics) reduced to
+// p x p.  The reference's resizer is `torchvision.transforms.Resize` (dataset.py imports torchvision.transforms as
+// v2): a uint8 tensor is cast to float32, resized by torch's antialiased bilinear kernel and rounded back
+// (round-half-to-even).  The antialiased kernel is a triangle filter whose support is the scale factor (3 input pixels
+// each side), applied separably — horizontal pass first — with per-output-pixel normalised float32 weights computed
+// exactly as aten does (UpSampleKernel.cpp `_compute_indices_min_size_weights_aa`): for the 3:1 ratio every interior
+// output has the five taps [1 2 3 2 1]/9 starting one pixel left of its 3-pixel cell; the first and last outputs lose
+// the tap outside the crop and are renormalised ([2 3 2 1]/8, [1 2 3 2]/8).  Each pass is the plain left-to-right
+// float32 sum x0*w0 + x1*w1 + ... (separate multiply and add, no contraction).  Results equal the reference's bytes
+// except at exact .5 ties of the filtered value, where torch's own output depends on whether its build fuses the
+// multiply-add for that pixel (AVX-512 main loop vs scalar tail) — about 1 pixel in 10^6 (tests/test_gpu_context.py).
+//
+// One CTA produces a 32 x 8 block of one band of one context tile: the 98 x 26 input window is gathered into shared
+// memory (zero filled outside the scene), reduced horizontally to 32 x 26 floats, then vertically to 32 x 8 bytes.
+// HBM traffic: 9 bytes read + 1 written per output pixel and band (the windows of neighbouring blocks overlap by 2).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cvcs {
+namespace {
+
+constexpr int kTapsMax = 6;
+struct Taps {
+    int off[3];            // first tap relative to 3*i, for i = 0 / interior / last
+    int n[3];              // taps in the row
+    float w[3][kTapsMax];  // normalised float32 weights
+};
+
+constexpr int kBX = 32, kBY = 8;                 // output block
+constexpr int kWX = 3 * kBX + 2, kWY = 3 * kBY + 2;   // input window (one extra tap each side)
+
+__global__ void __launch_bounds__(kThreads) context_kernel(const unsigned char* __restrict__ scene, int Cb, int H, int W,
+                                                           const int* __restrict__ tile_yx, const int* __restrict__ tile_slot,
+                                                           int p, unsigned char* __restrict__ out, Taps taps) {
+    __shared__ unsigned char win[kWY][kWX + 2];
+    __shared__ float hbuf[kWY][kBX];
+    const int bx = blockIdx.x * kBX, by = blockIdx.y * kBY;     // output block origin inside the tile
+    const int tile = blockIdx.z / Cb, band = blockIdx.z % Cb;
+    const int slot = tile_slot ? tile_slot[tile] : tile;
+    // crop origin in scene coordinates: (tly - p, tlx - p); window origin inside the crop: 3*b - 1
+    const long long cy0 = static_cast<long long>(tile_yx[2 * tile]) - p, cx0 = static_cast<long long>(tile_yx[2 * tile + 1]) - p;
+    const int wy0 = 3 * by - 1, wx0 = 3 * bx - 1;
+    const unsigned char* __restrict__ plane = scene + static_cast<size_t>(band) * H * W;
+    for (int i = threadIdx.x; i < kWY * kWX; i += kThreads) {
+        const int r = i / kWX, c = i - r * kWX;
+        const int yy = wy0 + r, xx = wx0 + c;                     // position inside the 3p x 3p crop
+        unsigned char v = 0;
+        if (yy >= 0 && yy < 3 * p && xx >= 0 && xx < 3 * p) {
+            const long long sy = cy0 + yy, sx = cx0 + xx;
+            if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = plane[sy * W + sx];
+        }
+        win[r][c] = v;
+    }
+    __syncthreads();
+    // horizontal pass: output column x of the block reads window columns 3*x + off + 1 ...
+    for (int i = threadIdx.x; i < kWY * kBX; i += kThreads) {
+        const int r = i / kBX, x = i - r * kBX;
+        const int ox = bx + x;
+        float acc = 0.f;
+        if (ox < p) {
+            const int row = ox == 0 ? 0 : (ox == p - 1 ? 2 : 1);
+            const int c0 = 3 * x + taps.off[row] + 1;
+            acc = __fmul_rn(static_cast<float>(win[r][c0]), taps.w[row][0]);
+            for (int k = 1; k < taps.n[row]; ++k) acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(win[r][c0 + k]), taps.w[row][k]));
+        }
+        hbuf[r][x] = acc;
+    }
+    __syncthreads();
+    {
+        const int x = threadIdx.x % kBX, y = threadIdx.x / kBX;
+        const int ox = bx + x, oy = by + y;
+        if (ox < p && oy < p) {
+            const int row = oy == 0 ? 0 : (oy == p - 1 ? 2 : 1);
+            const int r0 = 3 * y + taps.off[row] + 1;
+            float acc = __fmul_rn(hbuf[r0][x], taps.w[row][0]);
+            for (int k = 1; k < taps.n[row]; ++k) acc = __fadd_rn(acc, __fmul_rn(hbuf[r0 + k][x], taps.w[row][k]));
+            const float r = rintf(acc);                       // torch.round: half to even
+            out[((static_cast<size_t>(slot) * Cb + band) * p + oy) * p + ox] = static_cast<unsigned char>(r < 0.f ? 0.f : (r > 255.f ? 255.f : r));
+        }
+    }
+}
+
+// torch's antialias weights (aten UpSampleKernel.cpp `_compute_indices_min_size_weights_aa`, bilinear triangle filter),
+// float32 arithmetic throughout as aten does for float32 input, for input size 3p -> output size p.
+void taps_for(int p, int i, int* xmin_out, int* n_out, float* w_out) {
+    const float scale = static_cast<float>(3 * p) / static_cast<float>(p), support = scale;
+    const float invscale = 1.0f / scale;
+    const float center = scale * (static_cast<float>(i) + 0.5f);
+    int xmin = static_cast<int>(center - support + 0.5f);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5f);
+    if (xmax > 3 * p) xmax = 3 * p;
+    const int n = xmax - xmin;
+    volatile float tot = 0.f;
+    for (int j = 0; j < n; ++j) {
+        volatile float d = static_cast<float>(j + xmin) - center;
+        volatile float v = (d + 0.5f) * invscale;
+        if (v < 0.f) v = -v;
+        w_out[j] = v < 1.0f ? 1.0f - v : 0.0f;
+        tot = tot + w_out[j];
+    }
+    for (int j = 0; j < n; ++j) {
+        volatile float q = w_out[j] / tot;
+        w_out[j] = q;
+    }
+    *xmin_out = xmin;
+    *n_out = n;
+}
+
+}  // namespace
+
+int context_launch(const unsigned char* scene, int Cb, int H, int W, const int* tile_yx, const int* tile_slot, int n_tiles,
+                   int p, unsigned char* out, cudaStream_t stream) {
+    CVCS_REQUIRE(scene && tile_yx && out, "cvcs_tile_context: NULL argument");
+    CVCS_REQUIRE(Cb >= 1 && H > 0 && W > 0 && n_tiles >= 0 && p >= 3, "cvcs_tile_context: bad shape (Cb %d, %d x %d, %d tiles, p %d >= 3)", Cb, H, W, n_tiles, p);
+    if (n_tiles == 0) return CVCS_OK;
+    CVCS_REQUIRE(static_cast<long long>(n_tiles) * Cb <= 65535, "cvcs_tile_context: n_tiles * Cb = %lld exceeds the grid's z range; split the call",
+                 static_cast<long long>(n_tiles) * Cb);
+    Taps t{};
+    const int rows[3] = {0, 1, p - 1};
+    for (int r = 0; r < 3; ++r) {
+        float w[16];
+        int xmin = 0;
+        taps_for(p, rows[r], &xmin, &t.n[r], w);
+        while (t.n[r] > 1 && w[t.n[r] - 1] == 0.0f) --t.n[r];      // aten's tap range ends on a zero weight: x * 0 adds nothing
+        if (t.n[r] > 5) return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_tile_context: %d non-zero taps (the 98 x 26 window holds 5)", t.n[r]);
+        if (t.n[r] > kTapsMax) return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_tile_context: %d taps", t.n[r]);
+        t.off[r] = xmin - 3 * rows[r];
+        for (int j = 0; j < t.n[r]; ++j) t.w[r][j] = w[j];
+    }
+    dim3 grid((p + kBX - 1) / kBX, (p + kBY - 1) / kBY, n_tiles * Cb);
+    context_kernel<<<grid, kThreads, 0, stream>>>(scene, Cb, H, W, tile_yx, tile_slot, p, out, t);
+    CVCS_CUDA_OK(cudaGetLastError());
+    return CVCS_OK;
+}
+
+}  // namespace cvcs

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kThreads) confmat_kernel(const ConfParams p) {
             ++bad;
             return;
         }
-        acc.add_agg(static_cast<int>(t) * C + static_cast<int>(q));
+        acc.add(static_cast<int>(t) * C + static_cast<int>(q));
     };
     for (long long base = static_cast<long long>(blockIdx.x) * kThreads; base < nv;
          base += static_cast<long long>(gridDim.x) * kThreads) {
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kThreads) confmat_u8_kernel(const ConfParams p
             bad += n;
             return;
         }
-        acc.add_agg(t * C + q, n);
+        acc.add(t * C + q, n);
     };
     auto word = [&](uint32_t tw, uint32_t qw) {
         const int t0 = static_cast<int>(tw & 0xff), q0 = static_cast<int>(qw & 0xff);
@@ -662,6 +662,17 @@ int labels_prepare_launch(const long long* target, long long n, int C, long long
     if (blocks > kMaxGrid) blocks = kMaxGrid;
     if (blocks < 1) blocks = 1;
     weight_sum_kernel<<<static_cast<int>(blocks), kThreads, 0, stream>>>(p);
+    CVCS_CUDA_OK(cudaGetLastError());
+    return CVCS_OK;
+}
+
+static __global__ void reciprocal_kernel(const double* __restrict__ in, double* __restrict__ out) {
+    const double v = in[0];
+    out[0] = v;
+    out[1] = 1.0 / v;
+}
+int reciprocal_launch(const double* in, double* out2, cudaStream_t stream) {
+    reciprocal_kernel<<<1, 1, 0, stream>>>(in, out2);
     CVCS_CUDA_OK(cudaGetLastError());
     return CVCS_OK;
 }

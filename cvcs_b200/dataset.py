@@ -269,23 +269,19 @@ class IterableChunk(torch.utils.data.IterableDataset):
                                    out=color_out)
 
     def _contexts(self):
-        """``_get_context`` (dataset.py:11-16): the 3p x 3p neighbourhood, bilinearly resized to p.
-        The crop is K5; the resize is torchvision's on the GPU (not on the hot path: every shipped
-        net sets requires_context=False, nets.py:38,121,237,262,282,316)."""
-        import torchvision.transforms.v2 as v2
+        """``_get_context`` (dataset.py:11-16): the 3p x 3p neighbourhood of every tile of the chunk, reduced to p x p
+        by ``cvcs_tile_context`` (crop + the reference's antialiased bilinear Resize in one kernel, byte-identical;
+        one launch per scene, tiles scattered to their slots of the chunk batch)."""
         p, dev = self.p, self.device
-        resizer = v2.Resize(p, interpolation=v2.InterpolationMode.BILINEAR)
         n = len(self.chunk_crops)
         cb = self.images[0].shape[0]
         out = torch.empty((n, cb, p, p), dtype=torch.uint8, device=dev)
-        step = max(1, (256 << 20) // (cb * 9 * p * p))        # bound the 3p x 3p scratch to ~256 MB
         for s in range(self.chunk_size):
             slots = [i for i, so in enumerate(self.tile_scene) if so == s]
-            for k in range(0, len(slots), step):
-                part = slots[k:k + step]
-                yx = torch.tensor([(self.tile_yx[i][0] - p, self.tile_yx[i][1] - p) for i in part], dtype=torch.int32).to(dev)
-                big, _ = ops.tile_normalize(self.images[s], yx, (3 * p, 3 * p), out_dtype=torch.uint8)
-                out[torch.tensor(part, device=dev)] = resizer(big)
+            if not slots:
+                continue
+            yx = torch.tensor([self.tile_yx[i] for i in slots], dtype=torch.int32).to(dev)
+            ops.tile_context(self.images[s], yx, p, slots=torch.tensor(slots, dtype=torch.int32).to(dev), out=out)
         return out
 
     def _append_random_tps(self):
@@ -306,9 +302,7 @@ class IterableChunk(torch.utils.data.IterableDataset):
                 patch, index_mask = ops.tile_normalize(self.images[rand_index], yx, (aug_size, aug_size),
                                                        out_dtype=torch.uint8, label=self.index_masks[rand_index][0])
                 if self.load_context:
-                    cyx = torch.tensor([[random_y - p, random_x - p]], dtype=torch.int32, device=dev)
-                    big, _ = ops.tile_normalize(self.images[rand_index], cyx, (3 * p, 3 * p), out_dtype=torch.uint8)
-                    context = image_resizer(big)[0]
+                    context = ops.tile_context(self.images[rand_index], yx, p)[0]      # _get_context(…, random_y, random_x, p, …)
                 else:
                     context = none
                 patch = image_resizer(patch)[0]

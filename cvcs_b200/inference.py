@@ -75,11 +75,9 @@ class GID15(torch.utils.data.Dataset):
             padded_patch = padded[0]
         else:
             padded_patch = torch.tensor([0])
-        # context: 3p x 3p neighbourhood resized to p (dataset.py:11-16); torchvision's resize on the GPU crop
-        import torchvision.transforms.v2 as v2
-        cyx = torch.tensor([[tly - p, tlx - p]], dtype=torch.int32, device=self.device)
-        big, _ = ops.tile_normalize(self.last_image, cyx, (3 * p, 3 * p), out_dtype=torch.uint8)
-        context = v2.Resize(p)(big)[0]
+        # context: the 3p x 3p neighbourhood reduced to p (dataset.py:11-16, resizer dataset.py:65) — one kernel,
+        # byte-identical to the reference's crop + Resize
+        context = ops.tile_context(self.last_image, yx, p)[0]
         return tif_img[0], mask_img[0], context, padded_patch
 
 

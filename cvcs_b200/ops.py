@@ -213,14 +213,19 @@ def ce_fused(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.
              argmax: Optional[torch.Tensor] = None, confmat: Optional[torch.Tensor] = None,
              loss_sums: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None,
              total_weight: str = "given", xchg: Optional[Exchange] = None,
-             total_weight_out: Optional[torch.Tensor] = None):
+             total_weight_out: Optional[torch.Tensor] = None, local_total_weight: Optional[torch.Tensor] = None):
     """One fused pass. logits [B,C,H,W] f32/bf16 (contiguous or channels_last), target [B,H,W]
     u8/i64.  Returns (loss_out f32[1], loss_sums f64[3], dlogits or None).
 
     total_weight="given": the 'mean' divisor comes from inv_total_weight / inv_total_weight_dev (cvcs_ce_fused).
     total_weight="kernel": the kernel computes it from the labels itself — and, with ``xchg``, over all ranks' labels —
-    before it writes the first gradient (cvcs_ce_fused_tw); ``total_weight_out`` f64[2] receives {Σ, 1/Σ}."""
-    dev = _need_cuda(logits, target, weight, inv_total_weight_dev, dlogits, argmax, confmat, loss_sums, loss_out, total_weight_out)
+    before it writes the first gradient (cvcs_ce_fused_tw); ``total_weight_out`` f64[2] receives {Σ, 1/Σ}.  With
+    ``local_total_weight`` (f64[1] on the device, e.g. ``label_hist``'s total_weight_out[0:1] from a launch one step
+    ahead) the kernel skips its own label pre-pass and only exchanges."""
+    dev = _need_cuda(logits, target, weight, inv_total_weight_dev, dlogits, argmax, confmat, loss_sums, loss_out, total_weight_out,
+                     local_total_weight)
+    if local_total_weight is not None and (local_total_weight.dtype != torch.float64 or local_total_weight.numel() < 1):
+        raise RuntimeError("local_total_weight must be a float64 device tensor")
     if logits.dim() != 4:
         raise RuntimeError(f"cvcs_b200.ce_fused expects [B,C,H,W] logits, got {tuple(logits.shape)}")
     B, Cc, H, W = logits.shape
@@ -245,7 +250,7 @@ def ce_fused(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.
                 raise RuntimeError("total_weight_out must be a float64 tensor of 2 elements")
             check(lib.cvcs_ce_fused_tw(logits.data_ptr(), _tag(logits), layout, target.data_ptr(), _tag(target),
                                        _ptr(weight), ignore_index, B, Cc, H, W, xchg.handle if xchg is not None else None,
-                                       total_weight_out.data_ptr(), _ptr(dlogits) if want_grad else None, _ptr(argmax),
+                                       _ptr(local_total_weight), total_weight_out.data_ptr(), _ptr(dlogits) if want_grad else None, _ptr(argmax),
                                        _tag(argmax) if argmax is not None else _lib.U8, _ptr(confmat),
                                        loss_sums.data_ptr(), loss_out.data_ptr(), workspace(dev).data_ptr(), _stream(dev)))
         elif total_weight == "given":
@@ -288,14 +293,17 @@ def scale_inplace(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
 
 
 # ---- K2 / K3 ---------------------------------------------------------------------------------------
-def argmax(logits: torch.Tensor, out_dtype: torch.dtype = torch.int64) -> torch.Tensor:
+def argmax(logits: torch.Tensor, out_dtype: torch.dtype = torch.int64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """First-maximal class index over dim 1 of [B,C,H,W] logits (torch.max / argmax semantics)."""
-    dev = _need_cuda(logits)
+    dev = _need_cuda(logits, out)
     if logits.dim() != 4:
         raise RuntimeError(f"cvcs_b200.argmax expects [B,C,H,W], got {tuple(logits.shape)}")
     logits, layout = logits_layout(logits)
     B, Cc, H, W = logits.shape
-    out = torch.empty((B, H, W), dtype=out_dtype, device=dev)
+    if out is None:
+        out = torch.empty((B, H, W), dtype=out_dtype, device=dev)
+    elif out.numel() != B * H * W or not out.is_contiguous() or out.dtype not in (torch.uint8, torch.int64):
+        raise RuntimeError("argmax: `out` must be a contiguous uint8 / int64 tensor of B*H*W elements")
     with torch.cuda.device(dev):
         check(lib.cvcs_argmax(logits.data_ptr(), _tag(logits), layout, B, Cc, H, W, out.data_ptr(), _tag(out),
                               _stream(dev)))
@@ -359,24 +367,57 @@ def tile_normalize(scene: torch.Tensor, tile_yx: torch.Tensor, tile_hw: Tuple[in
     return out, label_out
 
 
+def tile_context(scene: torch.Tensor, tile_yx: torch.Tensor, p: int, *, slots: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``_get_context`` (dataset.py:11-16) for a batch of patch origins: scene u8 [Cb,H,W], tile_yx i32 [n,2] ->
+    u8 [n,Cb,p,p], the 3p x 3p neighbourhoods (zeros outside the scene) reduced to p x p with the reference's
+    antialiased bilinear uint8 resize, bit-identical."""
+    dev = _need_cuda(scene, tile_yx, slots, out)
+    assert scene.dtype == torch.uint8 and scene.dim() == 3 and scene.is_contiguous()
+    assert tile_yx.dtype == torch.int32 and tile_yx.dim() == 2 and tile_yx.shape[1] == 2 and tile_yx.is_contiguous()
+    Cb, H, W = scene.shape
+    n = tile_yx.shape[0]
+    if slots is not None:
+        assert slots.dtype == torch.int32 and slots.numel() == n and slots.is_contiguous() and out is not None
+    if out is None:
+        out = torch.empty((n, Cb, p, p), dtype=torch.uint8, device=dev)
+    else:
+        assert out.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape[1:]) == (Cb, p, p)
+    step = max(1, 65535 // Cb)
+    with torch.cuda.device(dev):
+        for k in range(0, n, step):
+            m = min(step, n - k)
+            check(lib.cvcs_tile_context(scene.data_ptr(), Cb, H, W, tile_yx[k:k + m].data_ptr(),
+                                        None if slots is None else slots[k:k + m].data_ptr(), m, p,
+                                        out.data_ptr() if slots is not None else out[k:k + m].data_ptr(), _stream(dev)))
+    return out
+
+
 # ---- N2 / N3 / N4 ----------------------------------------------------------------------------------
-def vote(maps: torch.Tensor, num_classes: int = 0, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+def vote(maps: torch.Tensor, num_classes: int = 0, out_dtype: Optional[torch.dtype] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Per-pixel majority vote over dim 0 (ties -> smallest index, as torch.mode)."""
-    dev = _need_cuda(maps)
+    dev = _need_cuda(maps, out)
     maps = maps.contiguous()
-    out = torch.empty(maps.shape[1:], dtype=out_dtype or maps.dtype, device=dev)
+    if out is None:
+        out = torch.empty(maps.shape[1:], dtype=out_dtype or maps.dtype, device=dev)
+    elif out.numel() != maps[0].numel() or not out.is_contiguous() or out.dtype not in (torch.uint8, torch.int64):
+        raise RuntimeError("vote: `out` must be a contiguous uint8 / int64 tensor with one element per pixel")
     with torch.cuda.device(dev):
         check(lib.cvcs_vote(maps.data_ptr(), _tag(maps), maps.shape[0], out.numel(), num_classes, out.data_ptr(),
                             _tag(out), _stream(dev)))
     return out
 
 
-def colorize(index_map: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
+def colorize(index_map: torch.Tensor, lut: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[H,W] class indices -> [H,W,3] f32 colours (GID15Converter.iconvert)."""
-    dev = _need_cuda(index_map, lut)
+    dev = _need_cuda(index_map, lut, out)
     index_map = index_map.contiguous()
     lut = lut.contiguous().to(torch.float32)
-    out = torch.empty((*index_map.shape, 3), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((*index_map.shape, 3), dtype=torch.float32, device=dev)
+    elif out.dtype != torch.float32 or out.numel() != index_map.numel() * 3 or not out.is_contiguous():
+        raise RuntimeError("colorize: `out` must be a contiguous float32 tensor of 3 values per pixel")
     with torch.cuda.device(dev):
         check(lib.cvcs_colorize(index_map.data_ptr(), _tag(index_map), index_map.numel(), lut.data_ptr(),
                                 lut.shape[0], out.data_ptr(), _stream(dev)))

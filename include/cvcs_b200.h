@@ -22,6 +22,7 @@
  *   cvcs_vote             <- Ensemble majority vote (torch.mode) utils.py:499-507
  *   cvcs_colorize         <- GID15Converter.iconvert            converters.py:23-36
  *   cvcs_stitch           <- tile re-assembly                   inference.py:40-57
+ *   cvcs_tile_context     <- _get_context (crop + v2.Resize)    dataset.py:11-16
  *   cvcs_host_*           <- the same calls on HOST buffers (copies inside), i.e. what a
  *                            non-torch caller binds; used for the end-to-end bench number.
  *
@@ -100,9 +101,9 @@ enum cvcs_option {
     CVCS_OPT_TMA_CTAS = 4,   /* CTAs per SM the TMA variant sizes its stages for (0 = default 2; 1..4)      */
     CVCS_OPT_TILE_CTAS = 5,  /* K5: CTAs per SM of the persistent grid (0 = default; 1..8)                  */
     CVCS_OPT_RESERVE_SMS = 6, /* K1: SMs left free (e.g. for an NCCL kernel that must run concurrently); 0..32   */
-    CVCS_OPT_PDL = 7,        /* K1 (TMA variant): 1 = launch with programmatic stream serialization (the kernel's
-                                prologue overlaps the tail of the previous kernel in the stream; it waits for that
-                                kernel before reading global memory)                                                  */
+    CVCS_OPT_PDL = 7,        /* K1 (TMA variant) launches with programmatic stream serialization (its prologue overlaps
+                                the tail of the previous kernel in the stream; the kernel waits for that kernel before
+                                it reads global memory, so results never change): 0 = default (on), 1 = on, 2 = off   */
     CVCS_OPT_COUNT = 8
 };
 int cvcs_set_option(int option, int value);
@@ -164,6 +165,9 @@ int cvcs_ce_fused(const void* logits_dev, int logits_dtype, int layout, const vo
  * exchange block over NVLink while every CTA waits for the peers' sums in its own block and adds them in rank order
  * (bit-identical total on every rank).  One launch per step; the collective is a handful of 8-byte peer stores.
  *   xchg                  nullable (single GPU); see below
+ *   local_total_weight_dev  nullable f64[1]: this rank's Σ v·w[y] if a cvcs_label_hist / cvcs_labels_prepare launch
+ *                         already produced it (e.g. one step ahead on another stream; any label dtype): the kernel then
+ *                         skips its label pre-pass and grid barrier and only performs the exchange
  *   total_weight_out_dev  nullable f64[2], overwritten with {Σ (global), 1/Σ}
  * Everything else as cvcs_ce_fused.  Shapes the TMA-staged kernel does not take (int64 labels, odd sizes, C > 21) run
  * as cvcs_label_hist + cvcs_ce_fused internally on one GPU (total_weight_out_dev required) and are refused with
@@ -171,7 +175,8 @@ int cvcs_ce_fused(const void* logits_dev, int logits_dtype, int layout, const vo
 typedef struct cvcs_xchg cvcs_xchg;
 int cvcs_ce_fused_tw(const void* logits_dev, int logits_dtype, int layout, const void* target_dev,
                      int target_dtype, const float* weight_dev, long long ignore_index, int B, int C,
-                     int H, int W, cvcs_xchg* xchg, double* total_weight_out_dev, void* dlogits_dev,
+                     int H, int W, cvcs_xchg* xchg, const double* local_total_weight_dev,
+                     double* total_weight_out_dev, void* dlogits_dev,
                      void* argmax_dev, int argmax_dtype, unsigned long long* confmat_dev,
                      double* loss_sums_dev, float* loss_out_dev, void* workspace_dev, void* stream);
 
@@ -238,6 +243,13 @@ int cvcs_tile_normalize(const unsigned char* scene_dev, int Cb, int H, int W,
                         void* workspace_dev, void* stream);
 
 /* ---- "next" rows ------------------------------------------------------------ */
+/* N4: the context view of patches (dataset.py:11-16 _get_context): for each patch origin (tly, tlx) the 3p x 3p
+ * neighbourhood crop(image, tly - p, tlx - p, 3p, 3p) (zeros outside the scene) reduced to p x p exactly as the
+ * reference's v2.Resize(p) does on a uint8 tensor (antialiased bilinear, horizontal pass first, Pillow-style fixed
+ * point) — bit-identical bytes.  scene u8 [Cb,H,W]; tile_yx i32 [n,2] PATCH origins; out u8 [n (or slots), Cb, p, p];
+ * tile_slot as in cvcs_tile_normalize.  p >= 3, n_tiles * Cb <= 65535 per call. */
+int cvcs_tile_context(const unsigned char* scene_dev, int Cb, int H, int W, const int* tile_yx_dev,
+                      const int* tile_slot_dev, int n_tiles, int p, unsigned char* out_dev, void* stream);
 /* N3: per-pixel majority vote over n_maps index maps (u8 or i64, [n_maps, n_pixels]);
  * ties -> smallest class index (torch.mode). */
 int cvcs_vote(const void* maps_dev, int dtype, int n_maps, long long n_pixels, int C, void* out_dev,

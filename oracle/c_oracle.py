@@ -136,3 +136,20 @@ def stitch(tiles: np.ndarray, yx: np.ndarray, H: int, W: int, crop: Optional[Tup
     f.argtypes = [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64]
     f(_p(tiles), n, th, tw, _p(yx), ch, cw, _p(scene), H, W)
     return scene
+
+
+def context(scene: np.ndarray, yx: np.ndarray, p: int, return_pre: bool = False):
+    """dataset.py:11-16 _get_context for a batch of patch origins: u8 [n,Cb,p,p] (and, on request, the float32 values
+    before rounding — the reference's own byte is only defined up to its FMA behaviour where they sit on a .5 tie)."""
+    scene = np.ascontiguousarray(scene, dtype=np.uint8)
+    yx = np.ascontiguousarray(yx, dtype=np.int32)
+    Cb, H, W = scene.shape
+    n = yx.shape[0]
+    out = np.empty((n, Cb, p, p), dtype=np.uint8)
+    pre = np.empty((n, Cb, p, p), dtype=np.float32) if return_pre else None
+    f = clib().oracle_context
+    f.restype = C.c_int
+    f.argtypes = [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp]
+    rc = f(_p(scene), Cb, H, W, _p(yx), n, p, _p(out), _p(pre))
+    assert rc == 0, rc
+    return (out, pre) if return_pre else out

@@ -221,3 +221,85 @@ void oracle_stitch(const uint8_t* tiles, int64_t n, int64_t th, int64_t tw, cons
                 scene[sy * W + sx] = tiles[(k * th + oy + y) * tw + ox + x];
             }
 }
+
+/* dataset.py:11-16 _get_context: crop(image, tly - p, tlx - p, 3p, 3p) — zeros outside the scene — then the
+ * reference's resizer (dataset.py:65,131; `v2` there is torchvision.transforms, the v1 API): uint8 -> float32,
+ * torch's antialiased bilinear interpolate, torch.round (half to even), back to uint8
+ * (torchvision/transforms/_functional_tensor.py resize: _cast_squeeze_in / interpolate(antialias=True) / _cast_squeeze_out).
+ * The antialiased kernel (aten/src/ATen/native/cpu/UpSampleKernel.cpp `_compute_indices_min_size_weights_aa` with the
+ * triangle filter, `basic_loop_aa_horizontal/vertical<float>`), all in float32: per output index i of an axis scaled
+ * by s = in/out (= 3): centre c = s (i + 1/2), support s, taps j in [max(0, int(c - s + 1/2)), min(in, int(c + s + 1/2))),
+ * weight max(0, 1 - |(j - c + 1/2) / s|) normalised to sum 1; each pass is x0 w0 + x1 w1 + ... left to right;
+ * horizontal pass first.  Pinned against the reference itself: tests/golden/context_cases.npz (equal except at exact .5
+ * ties of the filtered value, where torch's own rounding depends on FMA contraction in its vectorised loop).
+ * scene u8 [Cb,H,W]; yx i32 [n,2] patch origins; out u8 [n,Cb,p,p]; pre (nullable) float [n,Cb,p,p] value before rounding. */
+static int ctx_taps(int64_t in, int64_t outn, int64_t i, int* xmin_out, float* w) {
+    const float scale = (float)in / (float)outn, support = scale;
+    const float invscale = 1.0f / scale;
+    const float center = scale * ((float)i + 0.5f);
+    int64_t xmin = (int64_t)(center - support + 0.5f), xmax = (int64_t)(center + support + 0.5f);
+    if (xmin < 0) xmin = 0;
+    if (xmax > in) xmax = in;
+    volatile float tot = 0.0f;
+    const int n = (int)(xmax - xmin);
+    for (int j = 0; j < n; ++j) {
+        volatile float d = (float)(j + xmin) - center;
+        volatile float v = (d + 0.5f) * invscale;
+        if (v < 0) v = -v;
+        w[j] = v < 1.0f ? 1.0f - v : 0.0f;
+        tot = tot + w[j];
+    }
+    for (int j = 0; j < n; ++j) {
+        volatile float q = w[j] / tot;
+        w[j] = q;
+    }
+    *xmin_out = (int)xmin;
+    return n;
+}
+
+int oracle_context(const uint8_t* scene, int64_t Cb, int64_t H, int64_t W, const int32_t* yx, int64_t n, int64_t p,
+                   uint8_t* out, float* pre) {
+    const int64_t in = 3 * p;
+    int* xmin = (int*)malloc(sizeof(int) * p);
+    int* cnt = (int*)malloc(sizeof(int) * p);
+    float* wf = (float*)malloc(sizeof(float) * p * 16);
+    uint8_t* crop = (uint8_t*)malloc((size_t)in * in);
+    float* hbuf = (float*)malloc(sizeof(float) * (size_t)in * p);
+    if (!xmin || !cnt || !wf || !crop || !hbuf) return -1;
+    for (int64_t i = 0; i < p; ++i) {
+        cnt[i] = ctx_taps(in, p, i, &xmin[i], wf + 16 * i);
+        if (cnt[i] > 16) return -2;
+    }
+    for (int64_t k = 0; k < n; ++k)
+        for (int64_t cb = 0; cb < Cb; ++cb) {
+            const int64_t cy0 = (int64_t)yx[2 * k] - p, cx0 = (int64_t)yx[2 * k + 1] - p;
+            for (int64_t y = 0; y < in; ++y)
+                for (int64_t x = 0; x < in; ++x) {
+                    const int64_t sy = cy0 + y, sx = cx0 + x;
+                    crop[y * in + x] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? scene[(cb * H + sy) * W + sx] : 0;
+                }
+            for (int64_t y = 0; y < in; ++y)
+                for (int64_t i = 0; i < p; ++i) {
+                    volatile float acc = (float)crop[y * in + xmin[i]] * wf[16 * i];
+                    for (int j = 1; j < cnt[i]; ++j) {
+                        volatile float t = (float)crop[y * in + xmin[i] + j] * wf[16 * i + j]; /* no contraction */
+                        acc = acc + t;
+                    }
+                    hbuf[y * p + i] = acc;
+                }
+            for (int64_t i = 0; i < p; ++i)
+                for (int64_t x = 0; x < p; ++x) {
+                    volatile float acc = hbuf[(int64_t)xmin[i] * p + x] * wf[16 * i];
+                    for (int j = 1; j < cnt[i]; ++j) {
+                        volatile float t = hbuf[((int64_t)xmin[i] + j) * p + x] * wf[16 * i + j];
+                        acc = acc + t;
+                    }
+                    const size_t o = (size_t)(((k * Cb + cb) * p + i) * p + x);
+                    if (pre) pre[o] = acc;
+                    float r = rintf(acc); /* default rounding mode: to nearest even, as torch.round */
+                    out[o] = (uint8_t)(r < 0.0f ? 0.0f : (r > 255.0f ? 255.0f : r));
+                }
+        }
+    free(xmin); free(cnt); free(wf); free(crop); free(hbuf);
+    return 0;
+}

@@ -20,6 +20,8 @@ oracle/ref_shim.py) or from the torch / torchvision call the cited reference lin
                      counts and weights (dataset.py:28-32,105-221,241-384); crop helpers with
                      out-of-bounds offsets (dataset.py:11-32); Normalize (nets.py:339-342)
   misc_cases.npz     GID15Converter.iconvert (converters.py:23-36); torch.mode vote (utils.py:504-507)
+  context_cases.npz  dataset._get_context (dataset.py:11-16) with the reference's own resizer (v2.Resize(p), dataset.py:65,131)
+                     on uint8 tv_tensors.Image scenes: interior, scene-border and partly-outside patch origins, p = 8 / 32 / 224
 """
 from __future__ import annotations
 
@@ -351,7 +353,35 @@ def misc_cases():
     np.savez_compressed(os.path.join(HERE, "misc_cases.npz"), **out)
 
 
+def context_cases():
+    """The context view of a patch, by the reference's own function and resizer objects (only written when run
+    separately with --context, so that regenerating it does not touch the other committed files)."""
+    import torchvision.transforms as v2            # the module dataset.py imports as v2
+    from torchvision import tv_tensors
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    for name, cb, H, W, p in (("p8", 4, 50, 70, 8), ("p32", 3, 160, 130, 32), ("p224", 4, 700, 900, 224)):
+        scene = tv_tensors.Image(torch.randint(0, 256, (cb, H, W), generator=g, dtype=torch.uint8))
+        # smooth structure as well as noise: half of the scene is a gradient + blocks
+        yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        scene[:, :, : W // 2] = ((yy * 3 + xx * 5)[:, : W // 2] % 256).to(torch.uint8)
+        resizer = v2.Resize(p, interpolation=v2.InterpolationMode.BILINEAR)     # dataset.py:131 (and :65 default)
+        origins = [(0, 0), (p, p), (H - p, W - p), (H // 2, W // 3), (-p // 2, 5), (H - 3, W - 3), (-p, 3 - p),
+                   (3, W - p - 1), (2 * p + 1, 0)]
+        ctx = [dataset._get_context(scene, tly, tlx, p, resizer) for tly, tlx in origins]
+        assert all(c.dtype == torch.uint8 and tuple(c.shape) == (cb, p, p) for c in ctx)
+        out[f"{name}.scene"] = scene.numpy()
+        out[f"{name}.yx"] = np.array(origins, dtype=np.int32)
+        out[f"{name}.p"] = np.int64(p)
+        out[f"{name}.context"] = torch.stack([torch.as_tensor(c) for c in ctx]).numpy()
+    np.savez_compressed(os.path.join(HERE, "context_cases.npz"), **out)
+    return sorted({k.split(".")[0] for k in out})
+
+
 if __name__ == "__main__":
+    if "--context" in sys.argv:
+        print("context cases:", context_cases())
+        sys.exit(0)
     names = ce_cases()
     argmax_cases()
     eval_cases()

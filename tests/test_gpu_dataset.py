@@ -130,3 +130,12 @@ def test_loader_shuffle_specify_and_context():
     for patch, index_mask, color_mask, context in chunk:
         assert patch.shape == (3, 32, 32) and index_mask.shape == (32, 32) and context.shape == (3, 32, 32)
         assert color_mask.tolist() == [0]
+    # the context of every regular tile = _get_context of its scene at its origin (dataset.py:154), byte for byte
+    L.specify([0, 1])
+    chunk = L.get_iterable_chunk(0)
+    scenes = [imgs[i].numpy() for i in L.chunks[0]]
+    for k, (patch, _, _, context) in enumerate(chunk):
+        s, (tly, tlx) = chunk.tile_scene[k], chunk.tile_yx[k]
+        want = c_oracle.context(scenes[s], np.array([[tly, tlx]], dtype=np.int32), 32)[0]
+        assert np.array_equal(context.cpu().numpy(), want)
+        assert np.array_equal(patch.cpu().numpy(), scenes[s][:, tly:tly + 32, tlx:tlx + 32])

@@ -189,3 +189,31 @@ def test_two_handles_of_one_process_wired_together():
     finally:
         a.close()
         b.close()
+
+
+def test_local_total_weight_given_only_the_exchange_runs_in_the_kernel():
+    """tw_mode 2: this rank's Σw comes from a K4 launch (any label dtype); the kernel skips its pre-pass and exchanges."""
+    from cvcs_b200 import ops
+    for label_dtype in (torch.uint8, torch.int64):
+        x, t, w = make_case(3, 7, 96, 64, seed=21, label_dtype=label_dtype)
+        l0, g0, tw0, cm0 = chain(x, t, w, 255)
+        local = torch.tensor([tw0[0]], dtype=torch.float64, device=DEV)
+        # single GPU: identical to the chain
+        tw = torch.zeros(2, dtype=torch.float64, device=DEV)
+        cm = torch.zeros((7, 7), dtype=torch.int64, device=DEV)
+        loss, _, d = ops.ce_fused(x, t, w, 255, total_weight="kernel", local_total_weight=local, total_weight_out=tw, confmat=cm)
+        torch.cuda.synchronize()
+        assert tw.cpu().numpy()[0] == tw0[0] and float(loss) == l0 and np.array_equal(d.float().cpu().numpy(), g0)
+        assert np.array_equal(cm.cpu().numpy(), cm0)
+        # two ranks: rank 1's value played from the host
+        rk = Ranks(2, 0)
+        try:
+            rk.me.poke(1, 1, 1000.0)
+            loss, _, d = ops.ce_fused(x, t, w, 255, total_weight="kernel", xchg=rk.me, local_total_weight=local, total_weight_out=tw)
+            torch.cuda.synchronize()
+            total = tw0[0] + 1000.0
+            assert tw.cpu().numpy()[0] == total and rk.me.state() == (1, 0)
+            g1 = d.float().cpu().numpy()
+            assert np.abs(g1 - g0 * (tw0[0] / total)).max() <= 2e-6 * np.abs(g0).max() * (tw0[0] / total)
+        finally:
+            rk.close()
