@@ -315,6 +315,18 @@ class Ctx:
             self.dist.barrier()
         torch.cuda.synchronize(self.dev)
 
+    def align_start(self):
+        """N > 1: the ranks leave a barrier up to ~100 us apart, and the max-over-ranks region would count that skew once
+        per pass.  All ranks share this host's clock: agree on a start instant a few milliseconds ahead and spin to it."""
+        if self.world == 1:
+            return
+        torch = self.torch
+        t0 = torch.tensor([time.time() + 0.0015], dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t0, op=self.dist.ReduceOp.MAX)
+        target = float(t0.item())
+        while time.time() < target:
+            pass
+
     def max_over_ranks(self, *vals):
         """Element-wise max over ranks of a few host floats (device-timed regions are compared on the device)."""
         if self.world == 1:
@@ -332,6 +344,16 @@ class Ctx:
             from cvcs_b200 import shard
             self._xchg = shard.WeightExchange(device=self.dev)
         return self._xchg.handle_for(self.dev)
+
+    def allreduce_pass_end(self, buf):
+        """Pass-end sums (loss table + C x C counts as f64): the one-shot exchange over peer-mapped memory when the vector is
+        short enough, else NCCL."""
+        if self.world == 1:
+            return
+        if buf.numel() <= 2048 and not self.args.nccl_pass_end:
+            self.exchange().allreduce_(buf)
+        else:
+            self.dist.all_reduce(buf)
 
     def set_k1_options(self, path="auto", stages=0, no_wait_hint=False, vecp=0, ctas=0, pdl=1, reserve=0):
         L = self.lib
@@ -361,7 +383,10 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
                         K1 runs); at N > 1 followed by an NCCL all-reduce of the 8-byte sum
       tw_mode "xchg"    the same K4, but the ranks' sums are exchanged INSIDE K1 over NVLink peer memory (no NCCL)
       tw_mode "kernel"  no K4 at all: K1 sums the weights in its own label pre-pass (grid barrier), then exchanges
-      tw_mode "auto"    "chain" on one GPU, "xchg" on several
+      tw_mode "pipe"    no K4 and no pre-pass on the critical path: launch i also sums the weights over batch i+1's labels
+                        (in its prologue, while its pipeline fills) and launch i+1 starts from that sum; across GPUs the
+                        ranks' sums are exchanged inside K1.  One launch per step, one stream.
+      tw_mode "auto"    "pipe" (u8 labels; int64 labels: "chain" on one GPU, "xchg" on several)
     Returns a result dict."""
     torch, dist, ops, dev, world = ctx.torch, ctx.dist, ctx.ops, ctx.dev, ctx.world
     label_dtype = label_dtype or wl.get("label_dtype", "u8")
@@ -380,11 +405,14 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
     ii = wl["ignore_index"]
     data_dependent_tw = wl["weighted"] or (0 <= ii <= 255) or label_dtype == "i64"
     if tw_mode == "auto":
-        tw_mode = "xchg" if world > 1 else "chain"
+        tw_mode = "pipe" if label_dtype == "u8" else ("xchg" if world > 1 else "chain")
     tw_kernel = grad and data_dependent_tw and tw_mode == "kernel" and label_dtype == "u8"
-    prepass_on = grad and data_dependent_tw and not tw_kernel
+    tw_pipe = grad and data_dependent_tw and tw_mode == "pipe" and label_dtype == "u8"
+    prepass_on = grad and data_dependent_tw and not tw_kernel and not tw_pipe
     tw_xchg = prepass_on and tw_mode in ("xchg", "kernel") and world > 1      # K4 locally, exchange inside K1
-    xchg = ctx.exchange() if ((tw_kernel or tw_xchg) and world > 1) else None
+    xchg = ctx.exchange() if ((tw_kernel or tw_xchg or tw_pipe) and world > 1) else None
+    nxt = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(2)] if tw_pipe else None
+    gstep = {"n": 0}                                             # pipe mode: batches are consumed in one global order
     twg = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(n_sets)] if tw_xchg else None
     # K4 pre-pass (Σ v·w[y] must be known before the first dlogit is written) runs ONE STEP AHEAD on its own
     # stream: the labels of the next batch are known while the current K1 runs (as in a training loop with a
@@ -427,10 +455,14 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
 
     def step(i, timed, last=False):
         j = i % n_sets
+        if tw_pipe:
+            g_ = gstep["n"]
+            gstep["n"] += 1
+            j = g_ % n_sets
         x, t = sets[j]
         inv, inv_dev = 0.0, None
         if grad:
-            if tw_kernel:
+            if tw_kernel or tw_pipe:
                 pass
             elif prepass_on:
                 if issued["upto"] < i:
@@ -450,6 +482,12 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
             ops.eval_fused(x, t, ii, argmax=am[j], confmat=confmat)
         elif tw_kernel:
             ops.ce_fused(x, t, weight, ii, want_grad=True, total_weight="kernel", xchg=xchg, total_weight_out=tws[j],
+                         dlogits=dl[j], argmax=am[j], confmat=confmat, loss_sums=sums_table[i % sums_rows], loss_out=loss_out)
+        elif tw_pipe:
+            # this launch divides by the sum launch g-1 computed for it (exchanged across ranks inside the kernel) and
+            # computes the next batch's sum for launch g+1
+            ops.ce_fused(x, t, weight, ii, want_grad=True, total_weight="kernel", xchg=xchg, local_total_weight=nxt[g_ % 2][0:1],
+                         total_weight_out=tws[j], next_target=sets[(g_ + 1) % n_sets][1], next_total_weight_out=nxt[(g_ + 1) % 2],
                          dlogits=dl[j], argmax=am[j], confmat=confmat, loss_sums=sums_table[i % sums_rows], loss_out=loss_out)
         elif tw_xchg:
             ops.ce_fused(x, t_k1, weight, ii_k1, want_grad=True, total_weight="kernel", xchg=xchg, local_total_weight=tw_sum[j],
@@ -471,8 +509,10 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
     def pass_end():
         if world > 1:
             pass_buf[sums_rows * 3:].copy_(confmat.view(-1))     # exact: counts << 2^53
-            dist.all_reduce(pass_buf)                             # every step's loss sums + the C x C matrix, one collective
+            ctx.allreduce_pass_end(pass_buf)                      # every step's loss sums + the C x C matrix, one exchange
 
+    if tw_pipe:
+        ops.label_hist(sets[0][1], C, ii, weight=weight, total_weight_out=nxt[0])    # the very first batch: one K4, untimed
     for i in range(warmup):
         step(i, False, last=(i == warmup - 1))
     pass_end()                                                    # warm the pass-end collective up too
@@ -484,6 +524,7 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
     ctx.fence(pre)                                                # line the ranks up right before the timed region
     if want_clocks:
         ctx.sampler.start()
+    ctx.align_start()
     start.record()
     host_t0 = time.perf_counter()
     for i in range(steps):
@@ -539,7 +580,9 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
                    "metrics_only": metrics_only, "layout": layout,
                    "l2": f"inputs larger than L2: {n_sets} rotating sets of {set_bytes / 1e6:.0f} MB",
                    "total_weight": ("computed inside K1 (label pre-pass + grid barrier" + (", exchanged across ranks over NVLink inside the kernel)" if xchg is not None else ")"))
-                   if tw_kernel else (("K4 pre-pass one step ahead on a side stream" + (", the ranks' sums exchanged inside K1 over NVLink peer memory" if tw_xchg
+                   if tw_kernel else "pipelined across launches: K1 of step i sums the weights over step i+1's labels in its prologue" + (
+                       "; the ranks' sums are exchanged inside K1 over NVLink peer memory" if xchg is not None else "") if tw_pipe
+                   else (("K4 pre-pass one step ahead on a side stream" + (", the ranks' sums exchanged inside K1 over NVLink peer memory" if tw_xchg
                                                                                         else (" + NCCL all-reduce" if world > 1 else "")))
                                       if prepass_on else "constant (nothing can be ignored)")},
         "_state": (sets, weight),
@@ -631,7 +674,7 @@ def measure_chain(ctx, name, wl, steps, warmup, *, per_launch_events=True, want_
     def pass_end():
         if world > 1:
             pass_buf[sums_rows * 3:].copy_(confmat.view(-1))
-            dist.all_reduce(pass_buf)
+            ctx.allreduce_pass_end(pass_buf)
 
     for i in range(warmup):
         step(i, False)
@@ -643,6 +686,7 @@ def measure_chain(ctx, name, wl, steps, warmup, *, per_launch_events=True, want_
     ctx.fence()
     if want_clocks:
         ctx.sampler.start()
+    ctx.align_start()
     start.record()
     host_t0 = time.perf_counter()
     for i in range(steps):
@@ -875,8 +919,9 @@ def main():
                          "the previous kernel's tail); per-launch events would serialise the launches, so K1's average launch time "
                          "is then timed region / steps.  0: plain launches with CUDA events around every one")
     ap.add_argument("--label-block", type=int, default=32, help="side of the constant label blocks (1 = i.i.d. labels)")
-    ap.add_argument("--tw-mode", default="auto", choices=["auto", "kernel", "chain", "xchg"],
-                    help="data dependent total weight (see measure_ce): auto = chain on one GPU, xchg on several")
+    ap.add_argument("--tw-mode", default="auto", choices=["auto", "pipe", "kernel", "chain", "xchg"],
+                    help="data dependent total weight (see measure_ce): auto = pipe for u8 labels")
+    ap.add_argument("--nccl-pass-end", action="store_true", help="A/B: all-reduce the pass-end sums with NCCL instead of the one-shot peer-memory exchange")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-copy-ref", action="store_true", help="skip the same-size torch copy reference measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -948,7 +993,8 @@ def main():
         cfg = {"workload": f"{args.workload}: {wl['desc']}"}
         cfg.update(res["config"])
         cfg.update({"parallelism": (f"dp{world}: tiles sharded per GPU; one all-reduce per pass carrying the [steps,3] f64 loss-sum "
-                                    "table and the CxC confusion matrix") if world > 1 else "single GPU",
+                                    "table and the CxC confusion matrix (" + ("NCCL" if args.nccl_pass_end else
+                                    "one-shot exchange over IPC-mapped peer memory, NVLink") + ")") if world > 1 else "single GPU",
                     "path": args.path, "pdl": args.pdl, "sms_reserved_for_collectives": reserve})
         line = {
             "metric": METRIC if kind != "tile" else "Gpixel/s tile gather + cast/normalise (K5)", "value": res["value"], "unit": UNIT,

@@ -53,8 +53,8 @@ SIGNATURES = {
     "cvcs_labels_prepare": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _vp, _vp, _vp]),
     "cvcs_ce_fused": (_i, [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _vp,
                            _vp, _vp, _vp]),
-    "cvcs_ce_fused_tw": (_i, [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp,
-                              _vp, _vp, _vp]),
+    "cvcs_ce_fused_tw": (_i, [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _i,
+                              _vp, _vp, _vp, _vp, _vp]),
     "cvcs_xchg_create": (_i, [C.POINTER(_vp), _i, _i]),
     "cvcs_xchg_local_handle": (_i, [_vp, _vp]),
     "cvcs_xchg_open_peer": (_i, [_vp, _i, _vp]),
@@ -62,6 +62,7 @@ SIGNATURES = {
     "cvcs_xchg_local_block": (_vp, [_vp]),
     "cvcs_xchg_state": (_i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "cvcs_xchg_poke": (_i, [_vp, _i, C.c_ulonglong, _d, _vp]),
+    "cvcs_xchg_allreduce_f64": (_i, [_vp, _vp, _i, _vp]),
     "cvcs_xchg_destroy": (_i, [_vp]),
     "cvcs_eval_fused": (_i, [_vp, _i, _i, _vp, _i, _ll, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "cvcs_scale_inplace": (_i, [_vp, _i, _ll, _vp, _vp]),

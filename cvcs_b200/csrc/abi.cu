@@ -51,6 +51,7 @@ int tile_launch(const unsigned char*, int, int, int, const int*, const int*, int
                 const unsigned char*, void*, int, unsigned long long*, int, long long, void*, cudaStream_t);
 int stitch_launch(const unsigned char*, int, int, int, const int*, int, int, unsigned char*, int, int, cudaStream_t);
 int context_launch(const unsigned char*, int, int, int, const int*, const int*, int, int, unsigned char*, cudaStream_t);
+int xchg_allreduce_launch(XchgRegion* const* peers, int world, int rank, double* buf, int n, cudaStream_t stream);
 int vote_launch(const void*, int, int, long long, int, void*, int, cudaStream_t);
 int colorize_launch(const void*, int, long long, const float*, int, float*, cudaStream_t);
 
@@ -161,8 +162,8 @@ int cvcs_xchg_create(cvcs_xchg** out, int world, int rank) {
     for (int q = 0; q < kXMaxRanks; ++q) { x->peer[q] = nullptr; x->opened[q] = false; }
     cudaError_t e = cudaGetDevice(&x->device);
     void* blk = nullptr;
-    if (e == cudaSuccess) e = cudaMalloc(&blk, sizeof(XchgBlock));     // its own allocation: an IPC handle maps whole allocations
-    if (e == cudaSuccess) e = cudaMemset(blk, 0, sizeof(XchgBlock));
+    if (e == cudaSuccess) e = cudaMalloc(&blk, sizeof(XchgRegion));     // its own allocation: an IPC handle maps whole allocations
+    if (e == cudaSuccess) e = cudaMemset(blk, 0, sizeof(XchgRegion));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         if (blk) cudaFree(blk);
@@ -224,6 +225,17 @@ int cvcs_xchg_poke(cvcs_xchg* x, int as_rank, unsigned long long seq, double val
     return CVCS_OK;
 }
 
+int cvcs_xchg_allreduce_f64(cvcs_xchg* x, double* buf_dev, int n, void* stream) {
+    CVCS_REQUIRE(x && buf_dev && n >= 1 && n <= kXWideN, "cvcs_xchg_allreduce_f64: 1 <= n <= %d doubles (got %d)", kXWideN, n);
+    if (x->world == 1) return CVCS_OK;
+    XchgRegion* peers[kXMaxRanks];
+    for (int q = 0; q < x->world; ++q) {
+        CVCS_REQUIRE(x->peer[q], "cvcs_xchg_allreduce_f64: the exchange block of rank %d is not mapped", q);
+        peers[q] = reinterpret_cast<XchgRegion*>(x->peer[q]);
+    }
+    return xchg_allreduce_launch(peers, x->world, x->rank, buf_dev, n, static_cast<cudaStream_t>(stream));
+}
+
 int cvcs_xchg_destroy(cvcs_xchg* x) {
     if (!x) return CVCS_OK;
     for (int q = 0; q < x->world; ++q)
@@ -236,11 +248,15 @@ int cvcs_xchg_destroy(cvcs_xchg* x) {
 
 int cvcs_ce_fused_tw(const void* logits_dev, int logits_dtype, int layout, const void* target_dev, int target_dtype,
                      const float* weight_dev, long long ignore_index, int B, int C, int H, int W, cvcs_xchg* xchg,
-                     const double* local_total_weight_dev, double* total_weight_out_dev, void* dlogits_dev, void* argmax_dev, int argmax_dtype,
+                     const double* local_total_weight_dev, double* total_weight_out_dev, const void* next_target_dev,
+                     long long next_n_pixels, double* next_total_weight_out_dev, void* dlogits_dev, void* argmax_dev, int argmax_dtype,
                      unsigned long long* confmat_dev, double* loss_sums_dev, float* loss_out_dev, void* workspace_dev,
                      void* stream) {
     TwRequest tw{};
     tw.tw_local = local_total_weight_dev;
+    tw.next_target = next_target_dev;
+    tw.next_n = next_n_pixels;
+    tw.next_tw_out = next_total_weight_out_dev;
     tw.tw_out = total_weight_out_dev;
     tw.world = 1;
     tw.rank = 0;

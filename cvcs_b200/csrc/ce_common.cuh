@@ -38,12 +38,20 @@ struct CeParams {
                                  // 2: this rank's Σ given in tw_local_dev (a K4 launch), exchange in the kernel
     const double* tw_local_dev;  // tw_mode 2: f64[1]
     double* tw_out;              // nullable f64[2]: {Σ v·w[y] (global), 1/Σ}
+    // software pipelining across launches: this launch also sums the weights over the NEXT batch's (u8) labels — in its
+    // prologue, while the first bulk loads are in flight — and its last CTA publishes {Σ, 1/Σ} for the next launch
+    const void* next_target;     // nullable
+    long long next_n;            // pixels in the next batch
+    double* next_tw_out;         // f64[2]
     int xworld, xrank;           // ranks taking part in the exchange (1 = this GPU only)
     XchgBlock* xpeer[kXMaxRanks];  // every rank's exchange block (xpeer[xrank] is the local one)
 };
 
 // what cvcs_ce_fused_tw asks of the launcher: compute the total weight in the kernel, optionally exchanged across ranks
 struct TwRequest {
+    const void* next_target;       // nullable: u8 labels of the NEXT batch, scanned by this launch
+    long long next_n;
+    double* next_tw_out;           // f64[2] {Σ v·w[y] of the next batch (this rank), 1/Σ}
     const double* tw_local;        // nullable: this rank's Σ v·w[y] already on the device (skips the label pre-pass)
     double* tw_out;                // nullable f64[2]
     int world, rank;
@@ -218,33 +226,59 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// One thread per CTA.  `writer` (one thread of the grid) publishes this rank's value to every rank's block; every caller
-// then waits for all ranks' values of this exchange in its OWN block and adds them in rank order.  A peer that never
-// arrives (or has overrun the ring) ends the wait after ~4 s with NaN and a count in errors — never a hang.
+// this rank's value of exchange number `seq` -> slot [seq % depth][rank] of every rank's block, then the flags
+__device__ __forceinline__ void xchg_publish(const CeParams& p, double mine, unsigned long long seq) {
+    const int slot = static_cast<int>(seq % kXDepth);
+    for (int q = 0; q < p.xworld; ++q) *reinterpret_cast<volatile double*>(&p.xpeer[q]->slots[slot][p.xrank]) = mine;
+    __threadfence_system();
+    for (int q = 0; q < p.xworld; ++q) st_release_sys_u32(&p.xpeer[q]->flags[slot][p.xrank], static_cast<unsigned int>(seq));
+}
+// One WARP per CTA (all 32 lanes call it, `mine` uniform).  The writer CTA publishes this rank's value to every rank's
+// block — lane q serves peer q, and only if the previous launch has not already done so (published >= seq) — then lane q
+// of every caller waits for rank q's value of this exchange in its OWN block, and the values are added in rank order
+// (shuffles), so that every rank and every CTA gets the bit-identical total after two memory round trips, whatever the
+// number of ranks.  A peer that never arrives (or has overrun the ring) ends the wait after ~4 s with NaN and a count in
+// errors — never a hang.
 __device__ __forceinline__ double xchg_total_weight(const CeParams& p, double mine, bool writer) {
+    const int lane = threadIdx.x & 31;
     XchgBlock* local = p.xpeer[p.xrank];
-    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&local->seq) + 1ull;
+    unsigned long long seq = 0ull, pub = 0ull;
+    if (lane == 0) {
+        seq = *reinterpret_cast<volatile unsigned long long*>(&local->seq) + 1ull;
+        pub = *reinterpret_cast<volatile unsigned long long*>(&local->published);
+    }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    pub = __shfl_sync(0xffffffffu, pub, 0);
     const int slot = static_cast<int>(seq % kXDepth);
     const unsigned int tag = static_cast<unsigned int>(seq);
-    if (writer) {
-        for (int q = 0; q < p.xworld; ++q) *reinterpret_cast<volatile double*>(&p.xpeer[q]->slots[slot][p.xrank]) = mine;
+    if (writer && pub < seq && lane < p.xworld) {
+        *reinterpret_cast<volatile double*>(&p.xpeer[lane]->slots[slot][p.xrank]) = mine;
         __threadfence_system();
-        for (int q = 0; q < p.xworld; ++q) st_release_sys_u32(&p.xpeer[q]->flags[slot][p.xrank], tag);
+        st_release_sys_u32(&p.xpeer[lane]->flags[slot][p.xrank], tag);
     }
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    double tot = 0.0;
-    for (int q = 0; q < p.xworld; ++q) {
-        while (ld_acquire_sys_u32(&local->flags[slot][q]) != tag) {
+    double v = 0.0;
+    bool failed = false;
+    if (lane < p.xworld) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys_u32(&local->flags[slot][lane]) != tag) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (t1 - t0 > 4000000000ull) {
-                atomicAdd(&local->errors, 1ull);
-                return __longlong_as_double(0x7ff8000000000000ll);
+                failed = true;
+                break;
             }
             __nanosleep(64);
         }
-        tot += *reinterpret_cast<volatile double*>(&local->slots[slot][q]);
+        if (!failed) v = *reinterpret_cast<volatile double*>(&local->slots[slot][lane]);
+    }
+    __syncwarp();
+    const bool any_failed = __any_sync(0xffffffffu, failed);
+    double tot = 0.0;
+    for (int q = 0; q < p.xworld; ++q) tot += __shfl_sync(0xffffffffu, v, q);     // rank order
+    if (any_failed) {
+        if (lane == 0) atomicAdd(&local->errors, 1ull);
+        tot = __longlong_as_double(0x7ff8000000000000ll);
     }
     return tot;
 }
@@ -371,6 +405,16 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
     }
     a = warp_sum(a);
     b = warp_sum(b);
+    double next_sum = 0.0;
+    if (p.next_tw_out && warp == 0) {
+        // the next batch's total weight: per-CTA partials folded in a fixed order by one warp
+        for (unsigned int i = lane; i < gridDim.x; i += 32) next_sum += __ldcg(&p.ws->pre[1][i]);
+        next_sum = warp_sum(next_sum);
+        if (lane == 0) {
+            p.next_tw_out[0] = next_sum;
+            p.next_tw_out[1] = 1.0 / next_sum;
+        }
+    }
     sync();
     if (lane == 0) {
         red[warp] = a;
@@ -400,7 +444,16 @@ __device__ __forceinline__ void finish_loss(const CeParams& p, double lsum, doub
         p.ws->ticket = 0u;
         p.ws->next_chunk = 0u;
         p.ws->gbar = 0u;
-        if (p.tw_mode != 0 && p.xworld > 1) p.xpeer[p.xrank]->seq += 1ull;   // every CTA read it in its prologue, long ago
+        if (p.tw_mode != 0 && p.xworld > 1) {
+            XchgBlock* local = p.xpeer[p.xrank];
+            const unsigned long long seq = local->seq + 1ull;        // this launch's exchange; every CTA read it long ago
+            if (p.next_tw_out) {
+                // the NEXT exchange's value is known already: send it to the peers now, a whole step before they need it
+                xchg_publish(p, next_sum, seq + 1ull);
+                local->published = seq + 1ull;
+            }
+            local->seq = seq;
+        }
         __threadfence();
     }
 }

@@ -35,6 +35,12 @@ static int tw_fallback(CeParams p, int logits_dtype, int layout, int target_dtyp
         rc = label_hist_launch(p.target, target_dtype, p.n_pixels, p.C, p.ignore_index, nullptr, p.weight, p.tw_out, p.ws, stream);
     }
     if (rc) return rc;
+    if (p.next_target) {   // the next batch's sum as a launch of its own on this path
+        rc = label_hist_launch(p.next_target, CVCS_U8, p.next_n, p.C, p.ignore_index, nullptr, p.weight, p.next_tw_out, p.ws, stream);
+        if (rc) return rc;
+        p.next_target = nullptr;
+        p.next_tw_out = nullptr;
+    }
     p.tw_mode = 0;
     p.inv_tw_dev = p.tw_out + 1;
     const int forced = get_option(CVCS_OPT_CE_PATH);
@@ -103,10 +109,23 @@ int ce_fused_launch(const void* logits, int logits_dtype, int layout, const void
     p.status = status;
     p.no_loss = no_loss;
     p.xworld = 1;
+    if (tw && !dlogits && tw->next_target) {
+        // forward-only call inside a pipelined sequence: the next batch's sum still has to appear — as a launch of its own
+        CVCS_REQUIRE(tw->next_tw_out, "cvcs_ce_fused_tw: next_target needs next_total_weight_out_dev");
+        int rc = label_hist_launch(tw->next_target, CVCS_U8, tw->next_n, C, ignore_index, nullptr, weight, tw->next_tw_out, workspace, stream);
+        if (rc) return rc;
+    }
     if (tw && dlogits) {
         // total weight computed by K1 itself (label pre-pass + grid barrier [+ exchange]); forward-only calls do not need it
         CVCS_REQUIRE(tw->world >= 1 && tw->world <= kXMaxRanks && tw->rank >= 0 && tw->rank < tw->world,
                      "cvcs_ce_fused_tw: bad exchange geometry (world %d, rank %d)", tw->world, tw->rank);
+        if (tw->next_target) {
+            CVCS_REQUIRE(tw->next_tw_out && tw->next_n >= 0 && (reinterpret_cast<uintptr_t>(tw->next_target) % 16) == 0,
+                         "cvcs_ce_fused_tw: next_target needs next_total_weight_out_dev and 16-byte alignment");
+            p.next_target = tw->next_target;
+            p.next_n = tw->next_n;
+            p.next_tw_out = tw->next_tw_out;
+        }
         p.tw_mode = tw->tw_local ? 2 : 1;
         p.tw_local_dev = tw->tw_local;
         p.tw_out = tw->tw_out;

@@ -34,6 +34,7 @@ struct Geom {
     int wait_hint;     // 1: mbarrier waits pass a long suspend-time hint
     int stage_bytes;   // logits + labels, multiple of 128
     int label_off;     // offset of the labels inside a stage
+    int next_off;      // offset of the NEXT batch's label chunk inside a stage (0: not staged)
     int hist_off;      // offset of the bin accumulators in dynamic smem
     int stage_off;     // offset of stage 0
 };
@@ -177,38 +178,52 @@ __device__ __forceinline__ void sts_elem(unsigned char* base, int idx, float v) 
 // grid, cooperative launch), every CTA folds the per-CTA partials in the same fixed order, and with several GPUs one
 // thread publishes the sum to every peer over NVLink and every CTA adds the ranks' values in rank order.  The loader
 // warp is not involved: its first bulk loads are in flight meanwhile.  Called by threads 0..kThreads-1.
-template <int C>
-__device__ __forceinline__ double prepass_total_weight(const CeParams& p, int tid) {
-    __shared__ float wlut[256];
-    __shared__ double red[kWarps];
-    __shared__ double total;
+// Σ over this CTA's slice of n u8 labels of the 256-entry weight table; four 128-bit loads in flight per thread (the
+// labels come from HBM: latency-bound).  The block total is returned to thread 0.  Threads 0..kThreads-1.
+__device__ __forceinline__ double scan_label_weights(const float* wlut, double* red, const uint8_t* __restrict__ tgt, long long n, int tid) {
     const auto csync = [] { asm volatile("bar.sync %0, %1;" ::"n"(kConsumerBar), "n"(kThreads) : "memory"); };
-    wlut[tid] = (tid < C && static_cast<long long>(tid) != p.ignore_index) ? (p.weight ? p.weight[tid] : 1.0f) : 0.f;
-    csync();
-    const uint8_t* __restrict__ tgt = reinterpret_cast<const uint8_t*>(p.target);
-    const long long n16 = p.n_pixels / 16;
+    const long long n16 = n / 16;
     const long long per = (n16 + gridDim.x - 1) / gridDim.x;
     const long long lo = static_cast<long long>(blockIdx.x) * per;
     const long long hi = lo + per < n16 ? lo + per : n16;
     float a[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long i = lo + tid; i < hi; i += kThreads) {
-        const uint4 v = *reinterpret_cast<const uint4*>(tgt + 16 * i);     // default caching: stays in L2 for the main loop
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    constexpr int U = 4;
+    for (long long base = lo + tid; base < hi; base += U * kThreads) {
+        uint4 v[U];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) a[k & 3] += wlut[(w4[k / 4] >> (8 * (k % 4))) & 0xff];
+        for (int u = 0; u < U; ++u)     // default caching: the labels stay in L2 for the main loop
+            v[u] = base + u * kThreads < hi ? *reinterpret_cast<const uint4*>(tgt + 16 * (base + u * kThreads)) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (base + u * kThreads >= hi) continue;
+            const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k & 3] += wlut[(w4[k / 4] >> (8 * (k % 4))) & 0xff];
+        }
     }
     if (blockIdx.x == 0) {
         const long long i = n16 * 16 + tid;
-        if (i < p.n_pixels) a[0] += wlut[tgt[i]];
+        if (i < n) a[0] += wlut[tgt[i]];
     }
     double s = warp_sum(static_cast<double>((a[0] + a[1]) + (a[2] + a[3])));
     if ((tid & 31) == 0) red[tid >> 5] = s;
     csync();
+    double b = 0.0;
     if (tid == 0) {
-        double b = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) b += red[w];
-        p.ws->pre[blockIdx.x] = b;
+    }
+    csync();
+    return b;
+}
+
+template <int C>
+__device__ __forceinline__ double prepass_total_weight(const CeParams& p, float* wlut, double* red, int tid) {
+    __shared__ double total;
+    const auto csync = [] { asm volatile("bar.sync %0, %1;" ::"n"(kConsumerBar), "n"(kThreads) : "memory"); };
+    const double mine = scan_label_weights(wlut, red, reinterpret_cast<const uint8_t*>(p.target), p.n_pixels, tid);
+    if (tid == 0) {
+        p.ws->pre[0][blockIdx.x] = mine;
         __threadfence();
         atomicAdd(&p.ws->gbar, 1u);
         while (ld_acquire_gpu_u32(&p.ws->gbar) < gridDim.x) __nanosleep(32);
@@ -216,10 +231,10 @@ __device__ __forceinline__ double prepass_total_weight(const CeParams& p, int ti
     csync();
     if (tid < 32) {
         double v = 0.0;
-        for (unsigned int i = tid; i < gridDim.x; i += 32) v += __ldcg(&p.ws->pre[i]);   // same order in every CTA
+        for (unsigned int i = tid; i < gridDim.x; i += 32) v += __ldcg(&p.ws->pre[0][i]);   // same order in every CTA
         v = warp_sum(v);
+        if (p.xworld > 1) v = xchg_total_weight(p, v, blockIdx.x == 0);      // the whole warp
         if (tid == 0) {
-            if (p.xworld > 1) v = xchg_total_weight(p, v, blockIdx.x == 0);
             total = v;
             if (blockIdx.x == 0 && p.tw_out) {
                 p.tw_out[0] = v;
@@ -235,17 +250,30 @@ __device__ __forceinline__ double prepass_total_weight(const CeParams& p, int ti
 // exchange happens here, in the shadow of the pipeline fill.  Called by threads 0..kThreads-1.
 __device__ __forceinline__ double exchanged_total_weight(const CeParams& p, int tid) {
     __shared__ double total;
-    if (tid == 0) {
-        double v = __ldcg(p.tw_local_dev);
-        if (p.xworld > 1) v = xchg_total_weight(p, v, blockIdx.x == 0);
-        total = v;
-        if (blockIdx.x == 0 && p.tw_out) {
-            p.tw_out[0] = v;
-            p.tw_out[1] = 1.0 / v;
+    if (tid < 32) {
+        double v = __ldcg(p.tw_local_dev);                                     // uniform over the warp
+        if (p.xworld > 1) v = xchg_total_weight(p, v, blockIdx.x == 0);      // the whole warp
+        if (tid == 0) {
+            total = v;
+            if (blockIdx.x == 0 && p.tw_out) {
+                p.tw_out[0] = v;
+                p.tw_out[1] = 1.0 / v;
+            }
         }
     }
     asm volatile("bar.sync %0, %1;" ::"n"(kConsumerBar), "n"(kThreads) : "memory");
     return total;
+}
+
+// 256-entry weight table indexed by a label byte (0 for ignore_index and for anything >= C): static shared memory of
+// the kernels that call it (gradient kernels with a label pre-pass / next-batch scan); a constant address, no register
+__device__ __forceinline__ float* weight_lut() {
+    __shared__ float lut[256];
+    return lut;
+}
+__device__ __forceinline__ double* scan_scratch() {
+    __shared__ double red[kWarps];
+    return red;
 }
 
 template <int SUB>
@@ -340,7 +368,8 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                 desc[ring.s] = ck;
                 const uint32_t dst = stage0 + ring.s * g.stage_bytes;
                 const uint32_t lbytes = static_cast<uint32_t>(ck.n) * tsize;
-                mbar_expect_tx(bar, static_cast<uint32_t>(ck.n) * C * ES + lbytes);   // release: publishes desc
+                const uint32_t nbytes = g.next_off ? static_cast<uint32_t>(ck.n) : 0u;   // the next batch's labels of the same pixels
+                mbar_expect_tx(bar, static_cast<uint32_t>(ck.n) * C * ES + lbytes + nbytes);   // release: publishes desc
                 if constexpr (NHWC) {
                     bulk_g2s(dst, logits + ck.elem0, static_cast<uint32_t>(ck.n) * C * ES, bar);
                 } else {
@@ -349,6 +378,7 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                         bulk_g2s(dst + c * P * ES, logits + ck.elem0 + c * p.hw, static_cast<uint32_t>(ck.n) * ES, bar);
                 }
                 bulk_g2s(dst + g.label_off, target + ck.pix0 * tsize, lbytes, bar);
+                if (nbytes) bulk_g2s(dst + g.next_off, reinterpret_cast<const unsigned char*>(p.next_target) + ck.pix0, nbytes, bar);
                 // claim the next chunk now: the atomic's round trip overlaps the wait for the next stage
                 q = static_cast<long long>(gridDim.x) + atomicAdd(&p.ws->next_chunk, 1u);
                 ring.next(S);
@@ -394,10 +424,24 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
     } else {
         // ================= consumers =================
         if (tid < C) wsm[tid] = p.weight ? p.weight[tid] : 1.0f;
+        [[maybe_unused]] float next_acc = 0.f;   // Σ w over the next batch's labels this thread has seen
         float inv_tw = do_grad ? static_cast<float>(p.inv_tw_dev ? __ldcg(p.inv_tw_dev) : p.inv_tw) : 0.f;
         if constexpr (do_grad) {
-            if (p.tw_mode == 1) inv_tw = static_cast<float>(1.0 / prepass_total_weight<C>(p, tid));   // grid-wide; see above
-            else if (p.tw_mode == 2) inv_tw = static_cast<float>(1.0 / exchanged_total_weight(p, tid));
+            if (p.tw_mode == 1 || p.next_target) {
+                float* wlut = weight_lut();
+                double* scan_red = scan_scratch();
+                wlut[tid] = (tid < C && static_cast<long long>(tid) != p.ignore_index) ? (p.weight ? p.weight[tid] : 1.0f) : 0.f;
+                asm volatile("bar.sync %0, %1;" ::"n"(kConsumerBar), "n"(kThreads) : "memory");
+                if (p.next_target && !g.next_off) {
+                    // the NEXT batch's labels (a batch of another size: not staged with this one's chunks): summed now,
+                    // while the loader fills the pipeline; published by the last CTA
+                    const double nxt = scan_label_weights(wlut, scan_red, reinterpret_cast<const uint8_t*>(p.next_target), p.next_n, tid);
+                    if (tid == 0) p.ws->pre[1][blockIdx.x] = nxt;      // made visible by the loss epilogue's release
+                }
+
+                if (p.tw_mode == 1) inv_tw = static_cast<float>(1.0 / prepass_total_weight<C>(p, wlut, scan_red, tid));   // grid-wide; see above
+            }
+            if (p.tw_mode == 2) inv_tw = static_cast<float>(1.0 / exchanged_total_weight(p, tid));
         }
         // private counters: 16-bit, or 8-bit when a stage holds several sub-chunks (half the shared memory, which buys a
         // third stage for two CTAs per SM; a CTA of a 16-tile bf16 batch never reaches 255 pixels per thread anyway)
@@ -509,6 +553,23 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                         valid[k] = in_range && v != ign8;
                         tcl[k] = min(v, C - 1);
                         bad += (!in_range && v != ign8) ? 1u : 0u;
+                    }
+                }
+                if constexpr (do_grad) {
+                    if (g.next_off) {
+                        // the next batch's labels of these pixels arrived with the stage: four table look-ups per word
+                        const unsigned char* nl = stage + g.next_off + pix_t0;
+                        if constexpr (VECP % 4 == 0) {
+#pragma unroll
+                            for (int j = 0; j < VECP / 4; ++j) {
+                                const uint32_t w = *reinterpret_cast<const uint32_t*>(nl + 4 * j);
+                                const float* lut = weight_lut();
+                                next_acc += (lut[w & 0xffu] + lut[(w >> 16) & 0xffu]) + (lut[(w >> 8) & 0xffu] + lut[w >> 24]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < VECP; ++k) next_acc += weight_lut()[nl[k]];
+                        }
                     }
                 }
                 // ---- math.  fp32: one pixel at a time; bf16 NCHW: two pixels at a time, because a 32-bit
@@ -718,6 +779,20 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
 #ifdef CVCS_X_TIMING
         if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_loop));
 #endif
+        if constexpr (do_grad) {
+            if (g.next_off) {
+                __shared__ double next_red[kWarps];
+                const double v = warp_sum(static_cast<double>(next_acc));
+                if ((tid & 31) == 0) next_red[tid >> 5] = v;
+                Conf::sync();
+                if (tid == 0) {
+                    double b = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) b += next_red[w];
+                    p.ws->pre[1][blockIdx.x] = b;          // published by the loss epilogue's release
+                }
+            }
+        }
         if (do_conf) conf.flush(p.confmat);
         // the loss epilogue runs on the consumer warps alone: it overlaps the store warp's last bulk stores
         finish_loss<kWarps, kConsumerBar>(p, lsum, wsum, bad);
@@ -748,6 +823,11 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     Geom g{};
     g.label_off = C * P * ES;
     g.stage_bytes = ((g.label_off + P * tsize + 127) / 128) * 128;
+    if (p.dlogits && p.next_target && p.next_n == p.n_pixels) {
+        // the next batch has this batch's geometry: its label chunk rides in the stage (one more bulk copy per stage)
+        g.next_off = g.stage_bytes;
+        g.stage_bytes += ((P + 127) / 128) * 128;
+    }
     g.hist_off = 0;
     const int hist_bytes = p.confmat ? BinAcc<PRIV, 0, typename HistCounter<SUB>::type>::smem_bytes(C * C) : 0;
     g.stage_off = ((hist_bytes + 127) / 128) * 128;
@@ -812,6 +892,7 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
         if (reserve > 0 && reserve <= 32 && reserve < sms) grid -= (grid / sms) * reserve;
     }
     if (p.n_items < grid) grid = static_cast<int>(p.n_items < 1 ? 1 : p.n_items);
+    if ((p.tw_mode == 1 || p.next_target) && grid > kMaxPreGrid) grid = kMaxPreGrid;
     if (p.tw_mode == 1) {
         // the pre-pass meets at a grid-wide barrier: every CTA must be resident -> cooperative launch (the grid is the
         // persistent one, sized from the occupancy query, so the launch is refused rather than deadlocked if it is not)

@@ -32,6 +32,7 @@ int get_option(int option);  // cvcs_set_option values (0 = default / auto)
 // Zero-filled once by the caller; every kernel that uses a field restores it to zero.
 constexpr int kMaxHistBins = 1032;  // C <= 1024 plus {ignored, out-of-bounds}
 constexpr int kMaxGrid = 4096;  // upper bound on persistent grid size (148 SMs x <=16 CTAs, rounded)
+constexpr int kMaxPreGrid = 1024;  // the TMA-staged K1 runs at most 4 CTAs per SM
 struct Workspace {
     unsigned int ticket;          // last-block election counter
     unsigned int next_chunk;      // K1 (TMA variant): dynamic chunk claim counter
@@ -41,7 +42,7 @@ struct Workspace {
     unsigned long long pad1[5];
     double partial[2 * kMaxGrid]; // per-block {Σ w·nll, Σ w}
     unsigned long long hist[kMaxHistBins];  // per-call label histogram (K4 / K5), zero on exit
-    double pre[kMaxGrid];         // K1 pre-pass: per-block Σ v·w[y] (overwritten by every launch that uses it)
+    double pre[2][kMaxPreGrid];   // K1 (TMA variant) per-block Σ v·w[y]: [0] this batch's pre-pass, [1] the NEXT batch's scan
 };
 constexpr size_t kWorkspaceBytes = 128 * 1024;
 static_assert(sizeof(Workspace) <= kWorkspaceBytes, "workspace too small");
@@ -61,7 +62,9 @@ inline int shared_bin_replicas(int nbins, int budget_bytes = 64 * 1024, int hard
 // ---- Σw exchange block (one per rank, in device memory mapped into every peer: CUDA IPC over NVLink) ---------------
 // Rank r publishes its Σ v·w[y] of exchange number `seq` in slot [seq % kXDepth][r] of EVERY rank's block and then
 // releases flags[seq % kXDepth][r] = seq; a consumer spins on the N flags of its own block and adds the N values in
-// rank order, so every rank divides by the bit-identical total.  Depth 8: a rank may run up to 7 exchanges ahead of
+// rank order, so every rank divides by the bit-identical total.  A launch that also computed the NEXT batch's sum
+// (next_target) publishes it for exchange seq + 1 as it ends — a whole step ahead of its readers — so that in a
+// pipelined sequence no kernel ever waits for a peer.  Depth 8: a rank may run up to 7 exchanges ahead of
 // the slowest reader before it would overwrite an unread slot (a reader that finds a newer sequence number reports it).
 constexpr int kXDepth = 8;
 constexpr int kXMaxRanks = 16;
@@ -70,6 +73,22 @@ struct XchgBlock {
     unsigned int flags[kXDepth][kXMaxRanks];
     unsigned long long seq;        // exchanges completed by THIS rank (advanced by the last CTA of each launch)
     unsigned long long errors;     // time-outs / overruns seen by this rank's readers
+    unsigned long long published;  // highest exchange number whose value THIS rank has already sent to its peers
+};
+
+// Pass-end sums (the C x C confusion matrix, the per-step loss table): a one-shot all-reduce of up to kXWideN doubles
+// over the same peer-mapped allocation — every rank stores its vector into slot [parity][rank] of every rank's region,
+// releases a flag, waits for the N flags in its own region and adds the N vectors in rank order (bit-identical result
+// on every rank).  One 256-thread CTA, no NCCL kernel: ~10 us instead of a 50-100 us collective launch.
+constexpr int kXWideN = 2048;
+struct XchgWide {
+    double data[2][kXMaxRanks][kXWideN];
+    unsigned int flags[2][kXMaxRanks];
+    unsigned long long seq;
+};
+struct XchgRegion {
+    XchgBlock block;    // first: a peer pointer to the region is a pointer to its block
+    XchgWide wide;
 };
 
 constexpr float kLog2e = 1.4426950408889634f;

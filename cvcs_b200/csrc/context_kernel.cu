@@ -12,9 +12,10 @@
 // except at exact .5 ties of the filtered value, where torch's own output depends on whether its build fuses the
 // multiply-add for that pixel (AVX-512 main loop vs scalar tail) — about 1 pixel in 10^6 (tests/test_gpu_context.py).
 //
-// One CTA produces a 32 x 8 block of one band of one context tile: the 98 x 26 input window is gathered into shared
-// memory (zero filled outside the scene), reduced horizontally to 32 x 26 floats, then vertically to 32 x 8 bytes.
-// HBM traffic: 9 bytes read + 1 written per output pixel and band (the windows of neighbouring blocks overlap by 2).
+// One CTA produces a 32 x 32 block of one band of one context tile: the 98 x 98 input window is gathered into shared
+// memory row by row (one warp per row, zero filled outside the scene), reduced horizontally to 98 x 32 floats, then
+// vertically to 32 x 32 bytes.  HBM traffic: 9 bytes read + 1 written per output pixel and band (the windows of
+// neighbouring blocks overlap by 2 rows / columns).
 #include <math.h>
 
 #include "common.cuh"
@@ -29,14 +30,16 @@ struct Taps {
     float w[3][kTapsMax];  // normalised float32 weights
 };
 
-constexpr int kBX = 32, kBY = 8;                 // output block
+constexpr int kBX = 32, kBY = 32;                // output block
 constexpr int kWX = 3 * kBX + 2, kWY = 3 * kBY + 2;   // input window (one extra tap each side)
 
 __global__ void __launch_bounds__(kThreads) context_kernel(const unsigned char* __restrict__ scene, int Cb, int H, int W,
                                                            const int* __restrict__ tile_yx, const int* __restrict__ tile_slot,
-                                                           int p, unsigned char* __restrict__ out, Taps taps) {
+                                                           int p, unsigned char* __restrict__ out, const Taps taps_arg) {
     __shared__ unsigned char win[kWY][kWX + 2];
     __shared__ float hbuf[kWY][kBX];
+    __shared__ Taps taps;                      // indexed by row type at run time: shared memory, not a local-memory copy
+    if (threadIdx.x == 0) taps = taps_arg;
     const int bx = blockIdx.x * kBX, by = blockIdx.y * kBY;     // output block origin inside the tile
     const int tile = blockIdx.z / Cb, band = blockIdx.z % Cb;
     const int slot = tile_slot ? tile_slot[tile] : tile;
@@ -44,15 +47,16 @@ __global__ void __launch_bounds__(kThreads) context_kernel(const unsigned char* 
     const long long cy0 = static_cast<long long>(tile_yx[2 * tile]) - p, cx0 = static_cast<long long>(tile_yx[2 * tile + 1]) - p;
     const int wy0 = 3 * by - 1, wx0 = 3 * bx - 1;
     const unsigned char* __restrict__ plane = scene + static_cast<size_t>(band) * H * W;
-    for (int i = threadIdx.x; i < kWY * kWX; i += kThreads) {
-        const int r = i / kWX, c = i - r * kWX;
-        const int yy = wy0 + r, xx = wx0 + c;                     // position inside the 3p x 3p crop
-        unsigned char v = 0;
-        if (yy >= 0 && yy < 3 * p && xx >= 0 && xx < 3 * p) {
-            const long long sy = cy0 + yy, sx = cx0 + xx;
-            if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = plane[sy * W + sx];
+    for (int r = threadIdx.x >> 5; r < kWY; r += kThreads / 32) {
+        const int yy = wy0 + r;                                    // row inside the 3p x 3p crop
+        const long long sy = cy0 + yy;
+        const bool row_ok = yy >= 0 && yy < 3 * p && sy >= 0 && sy < H;
+        const unsigned char* __restrict__ src = plane + (row_ok ? sy : 0) * W;
+        for (int c = threadIdx.x & 31; c < kWX; c += 32) {
+            const int xx = wx0 + c;
+            const long long sx = cx0 + xx;
+            win[r][c] = (row_ok && xx >= 0 && xx < 3 * p && sx >= 0 && sx < W) ? src[sx] : static_cast<unsigned char>(0);
         }
-        win[r][c] = v;
     }
     __syncthreads();
     // horizontal pass: output column x of the block reads window columns 3*x + off + 1 ...
@@ -69,8 +73,8 @@ __global__ void __launch_bounds__(kThreads) context_kernel(const unsigned char* 
         hbuf[r][x] = acc;
     }
     __syncthreads();
-    {
-        const int x = threadIdx.x % kBX, y = threadIdx.x / kBX;
+    for (int i = threadIdx.x; i < kBY * kBX; i += kThreads) {
+        const int x = i % kBX, y = i / kBX;
         const int ox = bx + x, oy = by + y;
         if (ox < p && oy < p) {
             const int row = oy == 0 ? 0 : (oy == p - 1 ? 2 : 1);
@@ -126,7 +130,7 @@ int context_launch(const unsigned char* scene, int Cb, int H, int W, const int* 
         int xmin = 0;
         taps_for(p, rows[r], &xmin, &t.n[r], w);
         while (t.n[r] > 1 && w[t.n[r] - 1] == 0.0f) --t.n[r];      // aten's tap range ends on a zero weight: x * 0 adds nothing
-        if (t.n[r] > 5) return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_tile_context: %d non-zero taps (the 98 x 26 window holds 5)", t.n[r]);
+        if (t.n[r] > 5) return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_tile_context: %d non-zero taps (the input window holds 5)", t.n[r]);
         if (t.n[r] > kTapsMax) return set_error(CVCS_ERR_UNSUPPORTED, "cvcs_tile_context: %d taps", t.n[r]);
         t.off[r] = xmin - 3 * rows[r];
         for (int j = 0; j < t.n[r]; ++j) t.w[r][j] = w[j];

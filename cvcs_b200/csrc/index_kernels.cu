@@ -666,6 +666,64 @@ int labels_prepare_launch(const long long* target, long long n, int C, long long
     return CVCS_OK;
 }
 
+// ---- one-shot all-reduce of a short f64 vector over peer-mapped memory (pass-end sums) ------------------------------
+struct WidePeers {
+    XchgRegion* r[kXMaxRanks];
+};
+static __global__ void __launch_bounds__(kThreads) xchg_allreduce_kernel(const WidePeers peers, int world, int rank, double* __restrict__ buf, int n) {
+    __shared__ unsigned long long s_seq;
+    __shared__ int s_fail;
+    XchgRegion* local = peers.r[rank];
+    if (threadIdx.x == 0) {
+        s_seq = *reinterpret_cast<volatile unsigned long long*>(&local->wide.seq) + 1ull;
+        s_fail = 0;
+    }
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    const int par = static_cast<int>(seq & 1ull);
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const double v = buf[i];
+        for (int q = 0; q < world; ++q) *reinterpret_cast<volatile double*>(&peers.r[q]->wide.data[par][rank][i]) = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int q = 0; q < world; ++q)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&peers.r[q]->wide.flags[par][rank]), "r"(static_cast<unsigned int>(seq)) : "memory");
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int q = 0; q < world && !s_fail; ++q) {
+            for (;;) {
+                unsigned int f;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&local->wide.flags[par][q]) : "memory");
+                if (f == static_cast<unsigned int>(seq)) break;
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 4000000000ull) {       // a peer never arrived: NaN results and an error count, never a hang
+                    s_fail = 1;
+                    atomicAdd(&local->block.errors, 1ull);
+                    break;
+                }
+                __nanosleep(64);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        double s = 0.0;
+        for (int q = 0; q < world; ++q) s += *reinterpret_cast<volatile double*>(&local->wide.data[par][q][i]);   // rank order
+        buf[i] = s_fail ? __longlong_as_double(0x7ff8000000000000ll) : s;
+    }
+    if (threadIdx.x == 0) local->wide.seq = seq;
+}
+int xchg_allreduce_launch(XchgRegion* const* peers, int world, int rank, double* buf, int n, cudaStream_t stream) {
+    WidePeers wp{};
+    for (int q = 0; q < world; ++q) wp.r[q] = peers[q];
+    xchg_allreduce_kernel<<<1, kThreads, 0, stream>>>(wp, world, rank, buf, n);
+    CVCS_CUDA_OK(cudaGetLastError());
+    return CVCS_OK;
+}
+
 static __global__ void reciprocal_kernel(const double* __restrict__ in, double* __restrict__ out) {
     const double v = in[0];
     out[0] = v;

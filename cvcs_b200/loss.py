@@ -112,6 +112,8 @@ class FusedCrossEntropyLoss(nn.Module):
         self._w32: Optional[torch.Tensor] = None
         self._w32_key = None
         self._prefetched = None   # (target tensor, its version, num_classes, f64[2] total weight, ready event, u8 labels)
+        self._next_labels = None  # uint8 labels announced for the next batch: (tensor, version, num_classes)
+        self._scanned = None      # (tensor, version, num_classes, f64[2]) summed by the previous launch for THIS batch
         self._side: Optional[torch.cuda.Stream] = None
 
     # -- helpers -------------------------------------------------------------------------------------
@@ -126,10 +128,17 @@ class FusedCrossEntropyLoss(nn.Module):
         return self._w32
 
     def prefetch_total_weight(self, target: torch.Tensor, num_classes: int) -> None:
-        """Optional, int64 labels: start the label pre-pass (Σ v·w[y] + the byte copy of the labels) for ``target`` on a
-        side stream NOW — e.g. right after the batch is loaded, while the model's forward pass runs — so that the next
-        ``forward`` with this same, unmodified target tensor finds it done.  (uint8 labels need no pre-pass launch at
-        all: the fused kernel sums the weights itself.)"""
+        """Optional: announce the labels of the NEXT batch as soon as they are on the device.
+        int64 labels: the label pre-pass (Σ v·w[y] + the byte copy of the labels) starts NOW on a side stream — e.g.
+        while the model's forward pass runs — and the ``forward`` that receives this same, unmodified tensor finds it done.
+        uint8 labels: the next ``forward`` (of the CURRENT batch) sums the weights over them inside its own kernel launch
+        (``next_target``), so that the forward of this batch starts from a finished sum: the pre-pass is pipelined
+        across launches and never sits on the critical path."""
+        if target.is_cuda and target.dtype == torch.uint8 and target.is_contiguous():
+            # uint8 labels: no launch now — the NEXT forward call sums the weights over these labels inside its own
+            # kernel (staged with its chunks) and the call after that, on this very tensor, starts from that sum
+            self._next_labels = (target, target._version, num_classes)
+            return
         if not target.is_cuda or target.dtype != torch.int64 or num_classes > 254:
             return
         dev = target.device
@@ -198,8 +207,20 @@ class FusedCrossEntropyLoss(nn.Module):
         argmax = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if (self.return_argmax and C <= 256) else None
         if mode == "kernel":
             tw = torch.empty(2, dtype=torch.float64, device=dev)
+            local = None
+            sc = self._scanned
+            if sc is not None and sc[0] is target and sc[1] == target._version and sc[2] == C and t.dtype == torch.uint8:
+                local = sc[3][0:1]                                # the previous launch already summed this batch's weights
+            self._scanned = None
+            nt, nbuf = None, None
+            nl = self._next_labels
+            if nl is not None and nl[2] == C and nl[0]._version == nl[1] and nl[0].device == dev:
+                nt, nbuf = nl[0], torch.empty(2, dtype=torch.float64, device=dev)
+                self._scanned = (nl[0], nl[1], C, nbuf)
+            self._next_labels = None
             loss_out, sums, dlogits = ops.ce_fused(x, t, w, ii, want_grad=True, total_weight="kernel", xchg=xchg,
-                                                   total_weight_out=tw, argmax=argmax, confmat=conf)
+                                                   total_weight_out=tw, local_total_weight=local, next_target=nt,
+                                                   next_total_weight_out=nbuf, argmax=argmax, confmat=conf)
         else:
             loss_out, sums, dlogits = ops.ce_fused(x, t, w, ii, want_grad=want_grad, inv_total_weight=inv_tw,
                                                    inv_total_weight_dev=tw[1:] if (want_grad and tw is not None) else None,

@@ -176,6 +176,15 @@ class Exchange:
         with torch.cuda.device(self.device):
             check(lib.cvcs_xchg_poke(self.handle, int(as_rank), int(seq), float(value), _stream(self.device)))
 
+    def allreduce_(self, buf: torch.Tensor) -> torch.Tensor:
+        """In-place sum over the ranks of a short float64 device vector (<= 2048 elements), added in rank order — the
+        pass-end sums (confusion matrix, loss table) without an NCCL launch.  Every rank must call it equally often."""
+        if not buf.is_cuda or buf.dtype != torch.float64 or not buf.is_contiguous() or buf.numel() > 2048:
+            raise RuntimeError("Exchange.allreduce_: a contiguous float64 CUDA tensor of at most 2048 elements")
+        with torch.cuda.device(self.device):
+            check(lib.cvcs_xchg_allreduce_f64(self.handle, buf.data_ptr(), buf.numel(), _stream(self.device)))
+        return buf
+
     def close(self) -> None:
         if self._h:
             lib.cvcs_xchg_destroy(self._h)
@@ -213,7 +222,8 @@ def ce_fused(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.
              argmax: Optional[torch.Tensor] = None, confmat: Optional[torch.Tensor] = None,
              loss_sums: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None,
              total_weight: str = "given", xchg: Optional[Exchange] = None,
-             total_weight_out: Optional[torch.Tensor] = None, local_total_weight: Optional[torch.Tensor] = None):
+             total_weight_out: Optional[torch.Tensor] = None, local_total_weight: Optional[torch.Tensor] = None,
+             next_target: Optional[torch.Tensor] = None, next_total_weight_out: Optional[torch.Tensor] = None):
     """One fused pass. logits [B,C,H,W] f32/bf16 (contiguous or channels_last), target [B,H,W]
     u8/i64.  Returns (loss_out f32[1], loss_sums f64[3], dlogits or None).
 
@@ -221,11 +231,21 @@ def ce_fused(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.
     total_weight="kernel": the kernel computes it from the labels itself — and, with ``xchg``, over all ranks' labels —
     before it writes the first gradient (cvcs_ce_fused_tw); ``total_weight_out`` f64[2] receives {Σ, 1/Σ}.  With
     ``local_total_weight`` (f64[1] on the device, e.g. ``label_hist``'s total_weight_out[0:1] from a launch one step
-    ahead) the kernel skips its own label pre-pass and only exchanges."""
+    ahead) the kernel skips its own label pre-pass and only exchanges.  ``next_target`` (uint8 labels of the NEXT batch)
+    makes this launch also sum the weights over them into ``next_total_weight_out`` f64[2] — pass that as
+    ``local_total_weight`` of the next call and the pre-pass never sits on the critical path."""
     dev = _need_cuda(logits, target, weight, inv_total_weight_dev, dlogits, argmax, confmat, loss_sums, loss_out, total_weight_out,
                      local_total_weight)
     if local_total_weight is not None and (local_total_weight.dtype != torch.float64 or local_total_weight.numel() < 1):
         raise RuntimeError("local_total_weight must be a float64 device tensor")
+    if next_target is not None:
+        _need_cuda(next_target, next_total_weight_out)
+        if next_target.dtype != torch.uint8 or not next_target.is_contiguous():
+            raise RuntimeError("next_target must be a contiguous uint8 label tensor")
+        if next_total_weight_out is None or next_total_weight_out.dtype != torch.float64 or next_total_weight_out.numel() != 2:
+            raise RuntimeError("next_target needs next_total_weight_out: a float64 tensor of 2 elements")
+        if total_weight != "kernel":
+            raise RuntimeError("next_target is served by total_weight='kernel' (cvcs_ce_fused_tw)")
     if logits.dim() != 4:
         raise RuntimeError(f"cvcs_b200.ce_fused expects [B,C,H,W] logits, got {tuple(logits.shape)}")
     B, Cc, H, W = logits.shape
@@ -250,7 +270,8 @@ def ce_fused(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.
                 raise RuntimeError("total_weight_out must be a float64 tensor of 2 elements")
             check(lib.cvcs_ce_fused_tw(logits.data_ptr(), _tag(logits), layout, target.data_ptr(), _tag(target),
                                        _ptr(weight), ignore_index, B, Cc, H, W, xchg.handle if xchg is not None else None,
-                                       _ptr(local_total_weight), total_weight_out.data_ptr(), _ptr(dlogits) if want_grad else None, _ptr(argmax),
+                                       _ptr(local_total_weight), total_weight_out.data_ptr(), _ptr(next_target),
+                                       next_target.numel() if next_target is not None else 0, _ptr(next_total_weight_out), _ptr(dlogits) if want_grad else None, _ptr(argmax),
                                        _tag(argmax) if argmax is not None else _lib.U8, _ptr(confmat),
                                        loss_sums.data_ptr(), loss_out.data_ptr(), workspace(dev).data_ptr(), _stream(dev)))
         elif total_weight == "given":

@@ -138,6 +138,21 @@ class WeightExchange:
             raise RuntimeError(f"WeightExchange lives on {self.device}, tensors on {dev}")
         return self.x
 
+    def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
+        """Collectives (2) / (3) without NCCL: in-place sum over the ranks of a short float64 or int64 device tensor
+        (<= 2048 elements; int64 counts travel as float64, exact below 2^53), added in rank order.  COLLECTIVE."""
+        if self.world == 1:
+            return t
+        if t.dtype == torch.float64 and t.is_contiguous():
+            self.x.allreduce_(t.view(-1))
+            return t
+        if t.dtype != torch.int64:
+            raise TypeError(f"WeightExchange.all_reduce_: int64 or float64 expected, got {t.dtype}")
+        f = t.to(torch.float64).contiguous().view(-1)
+        self.x.allreduce_(f)
+        t.copy_(f.view(t.shape).to(torch.int64))
+        return t
+
     def state(self):
         """(exchanges completed, time-outs / overruns seen) on this rank — synchronises."""
         return self.x.state()

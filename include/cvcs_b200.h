@@ -169,6 +169,11 @@ int cvcs_ce_fused(const void* logits_dev, int logits_dtype, int layout, const vo
  *                         already produced it (e.g. one step ahead on another stream; any label dtype): the kernel then
  *                         skips its label pre-pass and grid barrier and only performs the exchange
  *   total_weight_out_dev  nullable f64[2], overwritten with {Σ (global), 1/Σ}
+ *   next_target_dev       nullable u8 labels (16-byte aligned, next_n_pixels of them) of the NEXT batch: this launch also
+ *                         sums the weights over them — in its prologue, while its first bulk loads are in flight — and
+ *                         writes {Σ, 1/Σ} (this rank's) to next_total_weight_out_dev f64[2] when it ends.  Passing that
+ *                         buffer as local_total_weight_dev of the next call pipelines the label pre-pass across
+ *                         launches: one launch per step, no pre-pass on the critical path, no second stream.
  * Everything else as cvcs_ce_fused.  Shapes the TMA-staged kernel does not take (int64 labels, odd sizes, C > 21) run
  * as cvcs_label_hist + cvcs_ce_fused internally on one GPU (total_weight_out_dev required) and are refused with
  * CVCS_ERR_UNSUPPORTED across GPUs.  Every rank of an exchange must make the same sequence of calls. */
@@ -176,7 +181,8 @@ typedef struct cvcs_xchg cvcs_xchg;
 int cvcs_ce_fused_tw(const void* logits_dev, int logits_dtype, int layout, const void* target_dev,
                      int target_dtype, const float* weight_dev, long long ignore_index, int B, int C,
                      int H, int W, cvcs_xchg* xchg, const double* local_total_weight_dev,
-                     double* total_weight_out_dev, void* dlogits_dev,
+                     double* total_weight_out_dev, const void* next_target_dev, long long next_n_pixels,
+                     double* next_total_weight_out_dev, void* dlogits_dev,
                      void* argmax_dev, int argmax_dtype, unsigned long long* confmat_dev,
                      double* loss_sums_dev, float* loss_out_dev, void* workspace_dev, void* stream);
 
@@ -193,6 +199,10 @@ int cvcs_xchg_set_peer(cvcs_xchg* x, int peer_rank, void* block_dev);
 void* cvcs_xchg_local_block(cvcs_xchg* x);
 int cvcs_xchg_state(cvcs_xchg* x, unsigned long long* seq_out, unsigned long long* errors_out);
 int cvcs_xchg_poke(cvcs_xchg* x, int as_rank, unsigned long long seq, double value, void* stream);
+/* Pass-end sums without a collective library: buf_dev[0..n) (f64, n <= 2048) is replaced by its sum over all ranks of the
+ * exchange, added in rank order (bit-identical on every rank); counts below 2^53 are exact.  One small kernel on
+ * `stream`; every rank must call it the same number of times.  Single-rank handles return at once. */
+int cvcs_xchg_allreduce_f64(cvcs_xchg* x, double* buf_dev, int n, void* stream);
 int cvcs_xchg_destroy(cvcs_xchg* x);
 
 /* ---- K1, metrics mode: argmax + confusion matrix straight from logits, no softmax / loss -----------

@@ -1,37 +1,44 @@
 #!/bin/bash
-# Round-end evidence run: smoke, full parity tests, default bench + reference arm, variants, kernel bench,
-# ncu launch list of the default bench, ncu --set full of the main kernels (exported to text/CSV on the box).
-TAG=${1:-r1c}
+# round-2 validation (run on a 2-GPU box): every GPU test, smoke(), the default bench line + its ncu launch list on GPU 0,
+# then the N = 2 multi-GPU suite.  Outputs under gpurun_out/ (copied to profiles/<tag>/ by hand).
 rm -rf gpurun_out/*; mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/summary.txt
+nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt
 timeout 2400 python -m pytest tests -m gpu -q --tb=short --timeout 600 -p no:cacheprovider > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/summary.txt
-tail -3 gpurun_out/pytest.log
-timeout 600 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench rc=$?" | tee -a gpurun_out/summary.txt
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.log 2>&1; echo "bench ref rc=$?" | tee -a gpurun_out/summary.txt
-for v in "" "--path direct" "--workload cfg3" "--workload cfg5" "--no-grad" "--metrics-only" "--metrics-only --workload cfg5" "--label-dtype i64" "--layout nhwc" "--layout nhwc --workload cfg3" "--layout nhwc --workload cfg5" "--batch 64" "--workload tile13" "--workload tile3"; do
-  echo "== $v" >> gpurun_out/bench_variants.log
-  timeout 300 python bench.py --steps 100 --warmup 10 --no-e2e --no-cpu-baseline $v >> gpurun_out/bench_variants.log 2>&1
-done
-timeout 300 python scripts/kernel_bench.py > gpurun_out/kernel_bench.jsonl 2> gpurun_out/kernel_bench.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_default.csv python bench.py > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?" | tee -a gpurun_out/summary.txt
-prof() {  # name, kernel regex, keep-rep(0/1), bench args...
-  local name=$1 rx=$2 keep=$3; shift 3
-  local cmd="python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-copy-ref $*"
-  timeout 300 $cmd > gpurun_out/plain_$name.log 2>&1 && \
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s 3 -c 1 -f -o gpurun_out/prof_$name $cmd > gpurun_out/ncu_$name.log 2>&1
-  echo "prof $name rc=$?" | tee -a gpurun_out/summary.txt
-  if [ -f gpurun_out/prof_$name.ncu-rep ]; then
-    ncu -i gpurun_out/prof_$name.ncu-rep --page raw --csv > gpurun_out/prof_$name.raw.csv 2>/dev/null
-    ncu -i gpurun_out/prof_$name.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/prof_$name.source.csv.gz
-    ncu -i gpurun_out/prof_$name.ncu-rep --page details > gpurun_out/prof_$name.details.txt 2>/dev/null
-    [ "$keep" = "1" ] || rm -f gpurun_out/prof_$name.ncu-rep
-  fi
-}
-prof cfg2 ce_tma 1
-prof cfg3 ce_tma 0 --workload cfg3
-prof cfg3_k4 weight_sum 0 --workload cfg3
-prof cfg5 ce_tma 0 --workload cfg5
-prof nograd ce_tma 0 --no-grad
-prof tile13 tile_kernel 0 --workload tile13
-du -sh gpurun_out
+tail -6 gpurun_out/pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/summary.txt; tail -1 gpurun_out/smoke.log
+timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?" | tee -a gpurun_out/summary.txt
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "bench ref rc=$?" | tee -a gpurun_out/summary.txt
+python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-1])
+    print('default:', round(d['value'],2), 'ms/step', round(d['ms_per_step'],4), 'frac', round(d['roofline']['frac'],3), 'e2e', d['e2e'] and round(d['e2e']['value'],3), 'e2e_eval', d['e2e_eval'] and round(d['e2e_eval']['value'],3), 'torch', d['torch_cuda_baseline'] and round(d['torch_cuda_baseline']['value'],2), 'cpu', d['cpu_baseline'] and round(d['cpu_baseline']['value'],4), 'launches', d['gpu_launches'], d['clocks'])
+    for k,v in (d.get('secondary') or {}).items():
+        print('  ', k, {kk:(round(vv,3) if isinstance(vv,float) else vv) for kk,vv in v.items() if kk in ('value','ms_per_step','error')}, 'frac', v.get('roofline',{}).get('frac') and round(v['roofline']['frac'],3), (v.get('torch_cuda_baseline') or {}).get('value'))
+    r=json.loads(open('gpurun_out/bench_reference.json').read().strip().splitlines()[-1])
+    print('reference arm:', r['value'], r['cpu_baseline'])
+except Exception as e: print('parse error', e)
+PY
+run() { echo "== $*" >> gpurun_out/sweep.log; timeout 200 python bench.py --steps 200 --warmup 20 --no-e2e --no-cpu-baseline --no-copy-ref --no-secondary --no-torch-cuda-baseline "$@" >> gpurun_out/sweep.log 2>&1; }
+run --workload cfg2
+run --workload cfg2 --pdl 0
+run --workload cfg3
+run --workload cfg3 --pdl 0
+run --workload cfg3 --tw-mode chain
+run --workload cfg2 --layout nhwc
+run --workload cfg3 --layout nhwc
+for b in 4 8 32 64; do run --workload cfg2 --batch $b; done
+python - <<'PY'
+import json
+for l in open('gpurun_out/sweep.log'):
+    if l.startswith('=='): print(l.strip()); continue
+    try: d=json.loads(l)
+    except Exception: print(l.strip()[:200]); continue
+    print('   ', round(d['value'],2), d['unit'], 'frac', round(d['roofline']['frac'],3), 'GB/s', round(d['roofline']['achieved'],1), 'k1 ms', round(d['roofline']['avg_launch_ms'],4), 'step ms', round(d['ms_per_step'],4))
+PY
+# ncu launch list of the default bench command (CPU leg skipped under the profiler): the kernel's SHARE of GPU time
+CMD="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-secondary"
+$CMD > gpurun_out/plain_default.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_default.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo "ncu launches rc=$?"
+bash scripts/gpu_multi.sh 2
+ls -la gpurun_out | head -50

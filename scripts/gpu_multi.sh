@@ -14,8 +14,10 @@ timeout 100 $TR --master-port 29514 scripts/h2d_probe.py > gpurun_out/h2d_probe_
 b() { name=$1; shift; timeout 300 $TR --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 "$@" > gpurun_out/bench_${name}_n$N.log 2>&1; echo "bench $name n$N rc=$?" | tee -a gpurun_out/summary_multi.txt; }
 b default
 b cfg3 --workload cfg3 --no-secondary
+if [ "$N" -le 2 ]; then
 b cfg3_nccl --workload cfg3 --no-secondary --tw-mode chain --no-e2e
 b cfg3_kernel --workload cfg3 --no-secondary --tw-mode kernel --no-e2e
+fi
 b cfg4 --workload cfg4
 b cfg5 --workload cfg5
 b cfg2_200 --steps 200 --warmup 20 --no-secondary --no-e2e

@@ -346,14 +346,29 @@ def test_prefetched_total_weight_gives_identical_results():
     ld = crit(xd, t)
     ld.backward()
     check(xd, ld, t)
-    # uint8 labels need no pre-pass launch: prefetching them is a no-op and the results still agree
-    t8 = t.to(torch.uint8)
-    crit.prefetch_total_weight(t8, C)
-    assert crit._prefetched is None
+    # uint8 labels: no launch at prefetch time — the forward of the batch BEFORE sums their weights inside its kernel
+    t8a, t8b = t.to(torch.uint8), t2.to(torch.uint8)
+    crit.prefetch_total_weight(t8b, C)                 # announce the next batch while the current one is t8a
+    assert crit._prefetched is None and crit._next_labels is not None
     xe = x.clone().requires_grad_(True)
-    le = crit(xe, t8)
+    le = crit(xe, t8a)                                 # this launch also scans t8b
     le.backward()
     check(xe, le, t)
+    assert crit._scanned is not None and crit._scanned[0] is t8b
+    xf = x.clone().requires_grad_(True)
+    lf = crit(xf, t8b)                                 # starts from the sum the previous launch left
+    lf.backward()
+    check(xf, lf, t2)
+    assert crit._scanned is None
+    # an announced tensor that is modified in place afterwards is not trusted
+    crit.prefetch_total_weight(t8a, C)
+    xg = x.clone().requires_grad_(True)
+    crit(xg, t8b).backward()
+    t8a[0, 50:60] = 1
+    xh = x.clone().requires_grad_(True)
+    lh = crit(xh, t8a)
+    lh.backward()
+    check(xh, lh, t8a)
 
 
 def test_module_edge_cases_from_the_review():

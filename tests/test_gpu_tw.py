@@ -217,3 +217,92 @@ def test_local_total_weight_given_only_the_exchange_runs_in_the_kernel():
             assert np.abs(g1 - g0 * (tw0[0] / total)).max() <= 2e-6 * np.abs(g0).max() * (tw0[0] / total)
         finally:
             rk.close()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_next_batch_scan_pipelines_the_pre_pass_across_launches(dtype):
+    """Launch i also sums the weights over batch i+1's labels; launch i+1 takes that as its local total weight.  Every
+    step must equal the plain K4 -> K1 chain on the same batch (bit-identical Σw hand-over, gradients to rounding)."""
+    from cvcs_b200 import ops
+    batches = [make_case(4, 7, 128, 128, seed=30 + i, dtype=dtype, frac_ignored=0.05 * (i + 1)) for i in range(4)]
+    w = batches[0][2]
+    nxt = [torch.zeros(2, dtype=torch.float64, device=DEV) for _ in range(2)]
+    tw = torch.zeros(2, dtype=torch.float64, device=DEV)
+    # first step: nothing was scanned ahead -> the kernel's own pre-pass, and it scans batch 1
+    for i, (x, t, _) in enumerate(batches):
+        t_next = batches[i + 1][1] if i + 1 < len(batches) else None
+        local = None if i == 0 else nxt[i % 2][0:1]
+        loss, _, d = ops.ce_fused(x, t, w, 255, total_weight="kernel", local_total_weight=local, total_weight_out=tw,
+                                  next_target=t_next, next_total_weight_out=nxt[(i + 1) % 2] if t_next is not None else None)
+        torch.cuda.synchronize()
+        l0, g0, tw0, _ = chain(x, t, w, 255)
+        assert abs(float(tw[0]) - tw0[0]) <= 1e-6 * tw0[0]
+        assert abs(float(loss) - l0) <= 1e-7 * abs(l0)
+        tol = 2e-6 if dtype == torch.float32 else 8e-3
+        assert np.abs(d.float().cpu().numpy() - g0).max() <= tol * np.abs(g0).max()
+        if t_next is not None:
+            # what the next launch will divide by: this rank's sum over the NEXT labels, as K4 computes it
+            twn = torch.zeros(2, dtype=torch.float64, device=DEV)
+            ops.label_hist(t_next, 7, 255, weight=w, total_weight_out=twn)
+            torch.cuda.synchronize()
+            assert abs(float(nxt[(i + 1) % 2][0]) - float(twn[0])) <= 1e-6 * float(twn[0])
+            assert abs(float(nxt[(i + 1) % 2][1]) * float(nxt[(i + 1) % 2][0]) - 1.0) < 1e-12
+    # forward-only call in the middle of a pipelined sequence still produces the next sum (as a launch of its own)
+    x, t, _ = batches[0]
+    out = torch.zeros(2, dtype=torch.float64, device=DEV)
+    ops.ce_fused(x, t, w, 255, want_grad=False, total_weight="kernel", next_target=batches[1][1], next_total_weight_out=out)
+    torch.cuda.synchronize()
+    twn = torch.zeros(2, dtype=torch.float64, device=DEV)
+    ops.label_hist(batches[1][1], 7, 255, weight=w, total_weight_out=twn)
+    torch.cuda.synchronize()
+    assert float(out[0]) == float(twn[0])
+
+
+def test_pipelined_sequence_publishes_the_next_sum_one_step_ahead():
+    """With an exchange AND next_target, the last CTA of launch i sends this rank's sum for exchange i+1 to the peers as
+    the launch ends; launch i+1 must not publish again and must still divide by (own + peers') of ITS batch."""
+    from cvcs_b200 import ops
+    batches = [make_case(2, 7, 128, 128, seed=40 + i, frac_ignored=0.1 * (i + 1)) for i in range(3)]
+    w = batches[0][2]
+    own = []
+    for x, t, _ in batches:
+        twn = torch.zeros(2, dtype=torch.float64, device=DEV)
+        ops.label_hist(t, 7, 255, weight=w, total_weight_out=twn)
+        torch.cuda.synchronize()
+        own.append(float(twn[0]))
+    peer = [111.0, 2222.0, 33333.0]
+    rk = Ranks(2, 0)
+    try:
+        nxt = [torch.zeros(2, dtype=torch.float64, device=DEV) for _ in range(2)]
+        tw = torch.zeros(2, dtype=torch.float64, device=DEV)
+        for i, (x, t, _) in enumerate(batches):
+            rk.me.poke(1, i + 1, peer[i])                      # rank 1's value of exchange i+1
+            t_next = batches[i + 1][1] if i + 1 < len(batches) else None
+            _, _, d = ops.ce_fused(x, t, w, 255, total_weight="kernel", xchg=rk.me, total_weight_out=tw,
+                                   local_total_weight=None if i == 0 else nxt[i % 2][0:1],
+                                   next_target=t_next, next_total_weight_out=nxt[(i + 1) % 2] if t_next is not None else None)
+            torch.cuda.synchronize()
+            total = float(tw[0])
+            assert abs(total - (own[i] + peer[i])) <= 1e-6 * total
+            _, g0, tw0, _ = chain(x, t, w, 255)
+            g1 = d.float().cpu().numpy()
+            assert np.abs(g1 - g0 * (tw0[0] / total)).max() <= 3e-6 * np.abs(g0).max() * (tw0[0] / total)
+            assert rk.me.state() == (i + 1, 0)
+            if t_next is not None:
+                # rank 1's block (the dummy peer) already holds this rank's value for the NEXT exchange
+                blk = rk.others[1]
+                assert blk is not None
+    finally:
+        rk.close()
+
+
+def test_single_rank_allreduce_is_the_identity():
+    from cvcs_b200 import ops
+    xc = ops.Exchange(1, 0, DEV)
+    try:
+        v = torch.arange(100, dtype=torch.float64, device=DEV)
+        assert torch.equal(xc.allreduce_(v.clone()), v)
+        with pytest.raises(RuntimeError):
+            xc.allreduce_(torch.zeros(10, device=DEV))            # float32: refused
+    finally:
+        xc.close()

@@ -113,6 +113,26 @@ def test_restated_confusion_matrix_equals_sklearn():
         assert np.array_equal(mi.compute().numpy(), confusion_matrix(t.numpy()[keep], p.numpy()[keep], labels=list(range(C))))
 
 
+def test_out_of_range_labels_against_sklearn():
+    """torchmetrics' validate_args path: values outside [0, C) that are not ignore_index.  sklearn with labels=range(C)
+    drops exactly those pairs; the oracle must count them (the product raises at compute()) and leave the same matrix —
+    with and without ignore_index=0, and with the out-of-range value on either side."""
+    from sklearn.metrics import confusion_matrix
+    g = torch.Generator().manual_seed(1)
+    for C in (3, 7, 16):
+        t = torch.randint(0, C, (4000,), generator=g).numpy()
+        p = torch.randint(0, C, (4000,), generator=g).numpy()
+        t[::97] = C + 3          # out-of-range targets
+        p[5::101] = C            # out-of-range predictions
+        t[7::89] = 255           # a LoveDA-style ignore label
+        for ign in (None, 0, 255):
+            keep = np.ones_like(t, dtype=bool) if ign is None else (t != ign)
+            ref = confusion_matrix(t[keep], p[keep], labels=list(range(C)))
+            n_bad = int(((t[keep] >= C) | (p[keep] >= C)).sum())
+            cm, bad = c_oracle.confmat(p, t, C, ign)
+            assert np.array_equal(cm, ref) and bad == n_bad and bad > 0
+
+
 @pytest.mark.parametrize("name", ["dense7", "absent_row", "absent_col", "row0_empty_col0_not", "big_counts", "diag"])
 def test_metric_formula_restatement(golden, name):
     g = golden("metrics_cases")
