@@ -355,7 +355,7 @@ class Ctx:
         else:
             self.dist.all_reduce(buf)
 
-    def set_k1_options(self, path="auto", stages=0, no_wait_hint=False, vecp=0, ctas=0, pdl=1, reserve=0):
+    def set_k1_options(self, path="auto", stages=0, no_wait_hint=False, vecp=0, ctas=0, pdl=1, reserve=0, l2_hint=0):
         L = self.lib
         L.set_option(L.OPT_CE_PATH, {"auto": 0, "tma": 1, "direct": 2, "generic": 3}[path])
         L.set_option(L.OPT_TMA_STAGES, stages)
@@ -364,6 +364,7 @@ class Ctx:
         L.set_option(L.OPT_TMA_CTAS, ctas)
         L.set_option(L.OPT_PDL, 1 if pdl else 2)
         L.set_option(L.OPT_RESERVE_SMS, reserve)
+        L.set_option(L.OPT_L2_HINT, l2_hint)
 
 
 def roofline_dict(ctx, achieved_gbs, bpp, px, k_ms, kernel, traffic_key, source, extra=None):
@@ -821,6 +822,57 @@ def torch_cuda_baseline(ctx, wl, state, steps=5, warmup=2):
             "ops": "torch.nn.CrossEntropyLoss fwd+bwd (int64 labels) + argmax(1) + bincount(t*C+p), torch " + torch.__version__}
 
 
+def graph_replay_rate(ctx, wl, state, steps=200):
+    """The small reference-shaped step is bound by the host's launch rate, not by the GPU: the same chain
+    (cvcs_labels_prepare on the int64 labels -> cvcs_ce_fused) captured ONCE into a CUDA graph — one rotation over the
+    input sets — and replayed shows what the device itself needs per step (every entry point takes
+    the caller's stream and neither synchronises nor allocates)."""
+    torch, ops, dev = ctx.torch, ctx.ops, ctx.dev
+    (sets, weight) = state
+    C, ii = wl["C"], wl["ignore_index"]
+    B, _, H, W = sets[0][0].shape
+    n = len(sets)
+    dl = [torch.empty_like(x) for x, _ in sets]
+    am = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    t8 = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in sets]
+    tws = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in sets]
+    cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
+    sums = torch.zeros((n, 3), dtype=torch.float64, device=dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def rotation():
+        for j, (x, t) in enumerate(sets):
+            if t.dtype == torch.int64:
+                ops.labels_prepare(t, C, ii, weight, tws[j], t8[j])
+                tk, ik = t8[j], 255
+            else:
+                ops.label_hist(t, C, ii, weight=weight, total_weight_out=tws[j])
+                tk, ik = t, ii
+            ops.ce_fused(x, tk, weight, ik, want_grad=True, inv_total_weight_dev=tws[j][1:2], dlogits=dl[j], argmax=am,
+                         confmat=cm, loss_sums=sums[j], loss_out=loss)
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        rotation()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        rotation()
+    replays = max(2, steps // n)
+    graph.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / (replays * n)
+    return {"value": B * H * W / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": replays * n, "gpu_launches_per_step": 2,
+            "how": f"one CUDA graph of {n} steps (labels_prepare + ce_fused each) replayed {replays} times"}
+
+
 def measure_e2e(ctx, wl, state, steps, grad=True, return_argmax=False):
     """The same step through the host-buffer C-ABI call: pinned host logits + labels in, loss + C x C (and optionally the
     u8 argmax map) back on the host, every step."""
@@ -888,6 +940,7 @@ def run_secondary(ctx, names, steps, warmup):
                 out[nm]["roofline"]["k5"] = rf["k5"]
             if nm == "ref" and ctx.world == 1:
                 out[nm]["torch_cuda_baseline"] = torch_cuda_baseline(ctx, WORKLOADS["ref"], r["_state"], steps=20, warmup=5)
+                out[nm]["graph_replay"] = graph_replay_rate(ctx, WORKLOADS["ref"], r["_state"])
             del r
         except Exception as e:                                   # a secondary must never take the primary line down
             out[nm] = {"error": f"{type(e).__name__}: {e}"[:300]}
@@ -918,6 +971,7 @@ def main():
                     help="1 (default, the library's default): K1 launches with programmatic stream serialization (its prologue overlaps "
                          "the previous kernel's tail); per-launch events would serialise the launches, so K1's average launch time "
                          "is then timed region / steps.  0: plain launches with CUDA events around every one")
+    ap.add_argument("--l2-hint", type=int, default=0, help="A/B: K1 L2 eviction hints (CVCS_OPT_L2_HINT: 0 default, v = bit mask v - 1)")
     ap.add_argument("--label-block", type=int, default=32, help="side of the constant label blocks (1 = i.i.d. labels)")
     ap.add_argument("--tw-mode", default="auto", choices=["auto", "pipe", "kernel", "chain", "xchg"],
                     help="data dependent total weight (see measure_ce): auto = pipe for u8 labels")
@@ -949,7 +1003,7 @@ def main():
     # a per-step collective (global Σw) has to run WHILE K1 runs: leave it two SMs (K1 claims chunks dynamically)
     reserve = args.reserve_sms if args.reserve_sms >= 0 else (2 if (world > 1 and data_dependent_tw and args.tw_mode == "chain") else 0)
     opts = dict(path=args.path, stages=args.stages, no_wait_hint=args.no_wait_hint, vecp=args.vecp, ctas=args.ctas,
-                pdl=args.pdl, reserve=reserve)
+                pdl=args.pdl, reserve=reserve, l2_hint=args.l2_hint)
     ctx.set_k1_options(**opts)
     if kind == "tile":
         ctx.lib.set_option(ctx.lib.OPT_TILE_CTAS, args.ctas)
@@ -995,7 +1049,7 @@ def main():
         cfg.update({"parallelism": (f"dp{world}: tiles sharded per GPU; one all-reduce per pass carrying the [steps,3] f64 loss-sum "
                                     "table and the CxC confusion matrix (" + ("NCCL" if args.nccl_pass_end else
                                     "one-shot exchange over IPC-mapped peer memory, NVLink") + ")") if world > 1 else "single GPU",
-                    "path": args.path, "pdl": args.pdl, "sms_reserved_for_collectives": reserve})
+                    "path": args.path, "pdl": args.pdl, "l2_hint": args.l2_hint, "sms_reserved_for_collectives": reserve})
         line = {
             "metric": METRIC if kind != "tile" else "Gpixel/s tile gather + cast/normalise (K5)", "value": res["value"], "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],

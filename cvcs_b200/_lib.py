@@ -96,7 +96,7 @@ def check(code: int) -> None:
         raise CvcsError(code, last_error())
 
 
-OPT_CE_PATH, OPT_TMA_STAGES, OPT_TMA_WAIT_HINT, OPT_TMA_VECP, OPT_TMA_CTAS, OPT_TILE_CTAS, OPT_RESERVE_SMS, OPT_PDL = 0, 1, 2, 3, 4, 5, 6, 7
+OPT_CE_PATH, OPT_TMA_STAGES, OPT_TMA_WAIT_HINT, OPT_TMA_VECP, OPT_TMA_CTAS, OPT_TILE_CTAS, OPT_RESERVE_SMS, OPT_PDL, OPT_L2_HINT = 0, 1, 2, 3, 4, 5, 6, 7, 8
 CE_PATH_AUTO, CE_PATH_TMA, CE_PATH_DIRECT, CE_PATH_GENERIC = 0, 1, 2, 3
 
 

@@ -218,8 +218,10 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// flag store of the fence + relaxed-store release pattern: ONE system-scope fence after the payload stores orders them
+// before every flag that follows (a st.release per peer would repeat the fence — microseconds each — once per rank)
+__device__ __forceinline__ void st_relaxed_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
     unsigned int v;
@@ -231,7 +233,7 @@ __device__ __forceinline__ void xchg_publish(const CeParams& p, double mine, uns
     const int slot = static_cast<int>(seq % kXDepth);
     for (int q = 0; q < p.xworld; ++q) *reinterpret_cast<volatile double*>(&p.xpeer[q]->slots[slot][p.xrank]) = mine;
     __threadfence_system();
-    for (int q = 0; q < p.xworld; ++q) st_release_sys_u32(&p.xpeer[q]->flags[slot][p.xrank], static_cast<unsigned int>(seq));
+    for (int q = 0; q < p.xworld; ++q) st_relaxed_sys_u32(&p.xpeer[q]->flags[slot][p.xrank], static_cast<unsigned int>(seq));
 }
 // One WARP per CTA (all 32 lanes call it, `mine` uniform).  The writer CTA publishes this rank's value to every rank's
 // block — lane q serves peer q, and only if the previous launch has not already done so (published >= seq) — then lane q
@@ -254,7 +256,7 @@ __device__ __forceinline__ double xchg_total_weight(const CeParams& p, double mi
     if (writer && pub < seq && lane < p.xworld) {
         *reinterpret_cast<volatile double*>(&p.xpeer[lane]->slots[slot][p.xrank]) = mine;
         __threadfence_system();
-        st_release_sys_u32(&p.xpeer[lane]->flags[slot][p.xrank], tag);
+        st_relaxed_sys_u32(&p.xpeer[lane]->flags[slot][p.xrank], tag);
     }
     double v = 0.0;
     bool failed = false;

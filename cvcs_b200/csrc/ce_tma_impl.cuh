@@ -35,6 +35,8 @@ struct Geom {
     int stage_bytes;   // logits + labels, multiple of 128
     int label_off;     // offset of the labels inside a stage
     int next_off;      // offset of the NEXT batch's label chunk inside a stage (0: not staged)
+    int l2_hint;       // bit 0: staged next-batch labels evict_last (the next launch re-reads them: 1 B/px of HBM saved),
+                       //        this batch's labels evict_first; bit 1: logits evict_first; bit 2: gradient stores evict_first
     int hist_off;      // offset of the bin accumulators in dynamic smem
     int stage_off;     // offset of stage 0
 };
@@ -100,9 +102,28 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy)
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 // shared -> global bulk copy, tracked by bulk async-groups
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* dst, uint32_t src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -351,6 +372,8 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
             // ---- loader
             Ring ring{0, 0u};
             long long q = blockIdx.x;
+            const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+            const bool hint_labels = (g.l2_hint & 1) != 0, hint_logits = (g.l2_hint & 2) != 0;
             for (long long i = 0;; ++i) {
                 if (i >= S) {
                     // the stage's previous occupant: stored away (grad) / consumed (forward only)
@@ -370,15 +393,32 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                 const uint32_t lbytes = static_cast<uint32_t>(ck.n) * tsize;
                 const uint32_t nbytes = g.next_off ? static_cast<uint32_t>(ck.n) : 0u;   // the next batch's labels of the same pixels
                 mbar_expect_tx(bar, static_cast<uint32_t>(ck.n) * C * ES + lbytes + nbytes);   // release: publishes desc
-                if constexpr (NHWC) {
-                    bulk_g2s(dst, logits + ck.elem0, static_cast<uint32_t>(ck.n) * C * ES, bar);
-                } else {
+                if (hint_logits) {
+                    if constexpr (NHWC) {
+                        bulk_g2s_hint(dst, logits + ck.elem0, static_cast<uint32_t>(ck.n) * C * ES, bar, pol_first);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        bulk_g2s(dst + c * P * ES, logits + ck.elem0 + c * p.hw, static_cast<uint32_t>(ck.n) * ES, bar);
+                        for (int c = 0; c < C; ++c)
+                            bulk_g2s_hint(dst + c * P * ES, logits + ck.elem0 + c * p.hw, static_cast<uint32_t>(ck.n) * ES, bar, pol_first);
+                    }
+                } else {
+                    if constexpr (NHWC) {
+                        bulk_g2s(dst, logits + ck.elem0, static_cast<uint32_t>(ck.n) * C * ES, bar);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+                            bulk_g2s(dst + c * P * ES, logits + ck.elem0 + c * p.hw, static_cast<uint32_t>(ck.n) * ES, bar);
+                    }
                 }
-                bulk_g2s(dst + g.label_off, target + ck.pix0 * tsize, lbytes, bar);
-                if (nbytes) bulk_g2s(dst + g.next_off, reinterpret_cast<const unsigned char*>(p.next_target) + ck.pix0, nbytes, bar);
+                if (hint_labels) {
+                    // the labels launch i stages for launch i+1's divisor are launch i+1's own labels: kept in L2 until
+                    // then (evict_last), released by their last reader (evict_first)
+                    bulk_g2s_hint(dst + g.label_off, target + ck.pix0 * tsize, lbytes, bar, pol_first);
+                    if (nbytes) bulk_g2s_hint(dst + g.next_off, reinterpret_cast<const unsigned char*>(p.next_target) + ck.pix0, nbytes, bar, pol_last);
+                } else {
+                    bulk_g2s(dst + g.label_off, target + ck.pix0 * tsize, lbytes, bar);
+                    if (nbytes) bulk_g2s(dst + g.next_off, reinterpret_cast<const unsigned char*>(p.next_target) + ck.pix0, nbytes, bar);
+                }
                 // claim the next chunk now: the atomic's round trip overlaps the wait for the next stage
                 q = static_cast<long long>(gridDim.x) + atomicAdd(&p.ws->next_chunk, 1u);
                 ring.next(S);
@@ -388,6 +428,8 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
             // as its store has finished reading shared memory — before blocking on the next `done`
             Ring ring{0, 0u};
             int pending = -1;  // stage whose store has been issued but not yet waited for
+            const uint64_t pol_first = l2_policy_evict_first();
+            const bool hint_grads = (g.l2_hint & 4) != 0;
             for (;;) {
                 const uint32_t done = bar0 + 8 * (kMaxStages + ring.s);
                 if (pending >= 0 && !mbar_test(done, ring.phase)) {
@@ -399,7 +441,15 @@ __global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CePa
                 const Chunk ck = desc[ring.s];
                 if (ck.n < 0) break;
                 const uint32_t src = stage0 + ring.s * g.stage_bytes;
-                if constexpr (NHWC) {
+                if (hint_grads) {
+                    if constexpr (NHWC) {
+                        bulk_s2g_hint(dlogits + ck.elem0, src, static_cast<uint32_t>(ck.n) * C * ES, pol_first);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+                            bulk_s2g_hint(dlogits + ck.elem0 + c * p.hw, src + c * P * ES, static_cast<uint32_t>(ck.n) * ES, pol_first);
+                    }
+                } else if constexpr (NHWC) {
                     bulk_s2g(dlogits + ck.elem0, src, static_cast<uint32_t>(ck.n) * C * ES);
                 } else {
 #pragma unroll
@@ -871,6 +921,10 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     }
     g.stages = stages;
     g.wait_hint = get_option(CVCS_OPT_TMA_WAIT_HINT) == 1 ? 0 : 1;
+    {
+        const int h = get_option(CVCS_OPT_L2_HINT);             // 0: default, v in 1..8: bits v - 1
+        g.l2_hint = (h >= 1 && h <= 8) ? h - 1 : (g.next_off ? 1 : 0);
+    }
     int smem = g.stage_off + stages * g.stage_bytes;
     // keep exactly `target_ctas` CTAs resident: the dynamic request is padded past what target + 1 could share
     // (more bytes in flight per SM than ~120 KB measurably lowers the sustained HBM rate)

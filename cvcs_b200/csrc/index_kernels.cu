@@ -212,6 +212,9 @@ __global__ void __launch_bounds__(kThreads) weight_sum_kernel(const HistParams p
             return v == p.ignore_index ? 255u : ((v >= 0 && v < C) ? static_cast<unsigned int>(v) : 254u);
         };
         constexpr int U = 4;
+        // the byte labels are read by the K1 launch that follows: ask L2 to keep them (16.8 MB for a 16-tile batch)
+        unsigned long long keep;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
         for (long long base = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; base < n2; base += U * stride) {
             Raw<16> r[U];
             bool have[U];
@@ -229,7 +232,9 @@ __global__ void __launch_bounds__(kThreads) weight_sum_kernel(const HistParams p
                 a[(u + 2) & 3] += w_of(v1);
                 if (p.narrow) {
                     const unsigned int c0 = code_of(v0), c1 = code_of(v1);
-                    __stcs(reinterpret_cast<unsigned short*>(p.narrow) + (base + u * stride), static_cast<unsigned short>(c0 | (c1 << 8)));
+                    asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(reinterpret_cast<unsigned short*>(p.narrow) + (base + u * stride)),
+                                 "h"(static_cast<unsigned short>(c0 | (c1 << 8))), "l"(keep)
+                                 : "memory");
                 }
             }
         }
@@ -689,7 +694,7 @@ static __global__ void __launch_bounds__(kThreads) xchg_allreduce_kernel(const W
     if (threadIdx.x == 0) {
         __threadfence_system();
         for (int q = 0; q < world; ++q)
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&peers.r[q]->wide.flags[par][rank]), "r"(static_cast<unsigned int>(seq)) : "memory");
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&peers.r[q]->wide.flags[par][rank]), "r"(static_cast<unsigned int>(seq)) : "memory");   // released by the fence above
         unsigned long long t0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         for (int q = 0; q < world && !s_fail; ++q) {

@@ -249,6 +249,14 @@ __global__ void __launch_bounds__(kThreads) tile_kernel_scalar(const TileParams 
     }
 }
 
+int simple_grid(long long n) {
+    long long blocks = (n + kThreads - 1) / kThreads;
+    long long g = static_cast<long long>(num_sms()) * 8;
+    if (g > blocks) g = blocks;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
 // ---- N2 stitch -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) stitch_kernel(const unsigned char* __restrict__ tiles, int n_tiles, int th,
                                                           int tw, const int* __restrict__ yx, int ch, int cw,
@@ -293,6 +301,45 @@ __global__ void __launch_bounds__(kThreads) stitch_x4_kernel(const unsigned char
     }
 }
 
+// 16 pixels per thread (one 128-bit load, one 128-bit store): everything a multiple of 16 — crop width and offset,
+// tile and scene width, the tile origins' x — which is the usual case (tiles of 224 / 256 / 1024 on a tile-sized grid).
+// A thread walks down `rows` consecutive rows of its 16-pixel column, so the index arithmetic is paid once per thread.
+__global__ void __launch_bounds__(kThreads) stitch_x16_kernel(const unsigned char* __restrict__ tiles, int n_tiles, int th,
+                                                              int tw, const int* __restrict__ yx, int ch, int cw,
+                                                              unsigned char* __restrict__ scene, int H, int W, int oy, int ox, int rows) {
+    const int gpr = cw / 16;                         // 16-pixel groups per cropped row
+    const int bands = (ch + rows - 1) / rows;        // row bands per tile
+    const long long per_tile = static_cast<long long>(bands) * gpr;
+    const long long total = per_tile * n_tiles;
+    for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * kThreads) {
+        const int t = static_cast<int>(i / per_tile);
+        const int r = static_cast<int>(i - t * per_tile);
+        const int band = r / gpr, x = (r - band * gpr) * 16;
+        const int y0 = band * rows;
+        const int sy0 = __ldg(yx + 2 * t) + y0, sx = __ldg(yx + 2 * t + 1) + x;
+        const unsigned char* src = tiles + (static_cast<long long>(t) * th + oy + y0) * tw + ox + x;
+        unsigned char* dst = scene + static_cast<long long>(sy0) * W + sx;
+        const int ny = min(rows, ch - y0);
+        const bool whole = sx >= 0 && sx + 15 < W && (sx & 15) == 0;
+#pragma unroll 4
+        for (int y = 0; y < ny; ++y) {
+            const int sy = sy0 + y;
+            if (sy < 0 || sy >= H) continue;
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src + static_cast<long long>(y) * tw));
+            unsigned char* d = dst + static_cast<long long>(y) * W;
+            if (whole) {
+                *reinterpret_cast<uint4*>(d) = v;
+            } else {
+                const unsigned int w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (sx + k >= 0 && sx + k < W) d[k] = static_cast<unsigned char>(w4[k >> 2] >> (8 * (k & 3)));
+            }
+        }
+    }
+}
+
 // ---- N3 vote -------------------------------------------------------------------------------------
 template <typename IT, typename OT>
 __global__ void __launch_bounds__(kThreads) vote_kernel(const IT* __restrict__ maps, int n_maps, long long n, OT* __restrict__ out) {
@@ -314,8 +361,66 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const IT* __restrict__ m
     }
 }
 
-// u8 maps, n_maps <= 8, n % 4 == 0, 4-byte aligned: each thread votes on 4 consecutive pixels; every map
-// is read exactly once (one 32-bit load per map) and the counting happens in registers.
+// u8 maps, n_maps <= 8: byte-parallel voting, four pixels per 32-bit word.  For every pair of maps one word
+// operation chain marks the byte lanes where they agree (exact zero-byte test of the XOR) and bumps both maps' per-lane
+// counters; the winner per pixel is the maximum of the 16-bit keys (count << 8 | 255 - value) — most frequent value,
+// ties to the smallest (torch.mode, utils.py:506) — taken two pixels at a time with the packed u16 max.  Every map is
+// read exactly once: a thread takes 16 consecutive pixels (one 128-bit load per map) or, in the tail kernel, 4.
+template <int NM>
+__device__ __forceinline__ uint32_t vote_word(const uint32_t (&w)[NM]) {
+    uint32_t cnt[NM];
+#pragma unroll
+    for (int a = 0; a < NM; ++a) cnt[a] = 0x01010101u;
+#pragma unroll
+    for (int a = 0; a < NM; ++a)
+#pragma unroll
+        for (int b = a + 1; b < NM; ++b) {
+            const uint32_t x = w[a] ^ w[b];
+            const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;          // bit 7 of a lane: its low 7 bits are non-zero
+            const uint32_t e = (~(t | x) & 0x80808080u) >> 7;            // 1 in the lanes where the two maps agree
+            cnt[a] += e;
+            cnt[b] += e;
+        }
+    uint32_t best_lo = 0u, best_hi = 0u;                                   // pixels (0, 1) and (2, 3) as u16 lanes
+#pragma unroll
+    for (int a = 0; a < NM; ++a) {
+        const uint32_t klo = __byte_perm(cnt[a], 0u, 0x1404) | (__byte_perm(w[a], 0u, 0x4140) ^ 0x00ff00ffu);
+        const uint32_t khi = __byte_perm(cnt[a], 0u, 0x3424) | (__byte_perm(w[a], 0u, 0x4342) ^ 0x00ff00ffu);
+        best_lo = __vmaxu2(best_lo, klo);
+        best_hi = __vmaxu2(best_hi, khi);
+    }
+    return ~__byte_perm(best_lo, best_hi, 0x6420);                         // the low byte of every lane is 255 - value
+}
+
+template <int NM>
+__global__ void __launch_bounds__(kThreads) vote_u8x16_kernel(const uint8_t* __restrict__ maps, long long n,
+                                                              uint8_t* __restrict__ out) {
+    const long long n16 = n / 16;
+    for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < n16;
+         i += static_cast<long long>(gridDim.x) * kThreads) {
+        uint4 v[NM];
+#pragma unroll
+        for (int a = 0; a < NM; ++a) v[a] = __ldcs(reinterpret_cast<const uint4*>(maps + a * n) + i);
+        uint4 res;
+        {
+            uint32_t w[NM];
+#pragma unroll
+            for (int a = 0; a < NM; ++a) w[a] = v[a].x;
+            res.x = vote_word<NM>(w);
+#pragma unroll
+            for (int a = 0; a < NM; ++a) w[a] = v[a].y;
+            res.y = vote_word<NM>(w);
+#pragma unroll
+            for (int a = 0; a < NM; ++a) w[a] = v[a].z;
+            res.z = vote_word<NM>(w);
+#pragma unroll
+            for (int a = 0; a < NM; ++a) w[a] = v[a].w;
+            res.w = vote_word<NM>(w);
+        }
+        __stcs(reinterpret_cast<uint4*>(out) + i, res);
+    }
+}
+
 template <int NM>
 __global__ void __launch_bounds__(kThreads) vote_u8x4_kernel(const uint8_t* __restrict__ maps, long long n,
                                                              uint8_t* __restrict__ out) {
@@ -325,39 +430,21 @@ __global__ void __launch_bounds__(kThreads) vote_u8x4_kernel(const uint8_t* __re
         uint32_t w[NM];
 #pragma unroll
         for (int a = 0; a < NM; ++a) w[a] = __ldcs(reinterpret_cast<const unsigned int*>(maps + a * n) + i);
-        uint32_t res = 0u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int v[NM];
-#pragma unroll
-            for (int a = 0; a < NM; ++a) v[a] = static_cast<int>((w[a] >> (8 * k)) & 0xff);
-            int best_v = 0, best_c = 0;
-#pragma unroll
-            for (int a = 0; a < NM; ++a) {
-                int cnt = 0;
-#pragma unroll
-                for (int b = 0; b < NM; ++b) cnt += (v[b] == v[a]) ? 1 : 0;
-                // most frequent value; ties -> smallest value (torch.mode)
-                const bool take = cnt > best_c || (cnt == best_c && v[a] < best_v);
-                best_c = take ? cnt : best_c;
-                best_v = take ? v[a] : best_v;
-            }
-            res |= static_cast<uint32_t>(best_v) << (8 * k);
-        }
-        __stcs(reinterpret_cast<unsigned int*>(out) + i, res);
+        __stcs(reinterpret_cast<unsigned int*>(out) + i, vote_word<NM>(w));
     }
 }
 
 template <int NM>
-bool try_vote_u8x4(const void* maps, int n_maps, long long n, void* out, cudaStream_t stream, int grid) {
+bool try_vote_u8x4(const void* maps, int n_maps, long long n, void* out, cudaStream_t stream, bool wide) {
     if constexpr (NM > 8) {
         return false;
     } else {
         if (n_maps == NM) {
-            vote_u8x4_kernel<NM><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const uint8_t*>(maps), n, reinterpret_cast<uint8_t*>(out));
+            if (wide) vote_u8x16_kernel<NM><<<simple_grid(n / 16), kThreads, 0, stream>>>(reinterpret_cast<const uint8_t*>(maps), n, reinterpret_cast<uint8_t*>(out));
+            else vote_u8x4_kernel<NM><<<simple_grid(n / 4), kThreads, 0, stream>>>(reinterpret_cast<const uint8_t*>(maps), n, reinterpret_cast<uint8_t*>(out));
             return true;
         }
-        return try_vote_u8x4<NM + 1>(maps, n_maps, n, out, stream, grid);
+        return try_vote_u8x4<NM + 1>(maps, n_maps, n, out, stream, wide);
     }
 }
 
@@ -383,13 +470,6 @@ __global__ void __launch_bounds__(kThreads) colorize_kernel(const IT* __restrict
     }
 }
 
-int simple_grid(long long n) {
-    long long blocks = (n + kThreads - 1) / kThreads;
-    long long g = static_cast<long long>(num_sms()) * 8;
-    if (g > blocks) g = blocks;
-    if (g < 1) g = 1;
-    return static_cast<int>(g);
-}
 
 }  // namespace
 
@@ -493,7 +573,13 @@ int stitch_launch(const unsigned char* tiles, int n_tiles, int th, int tw, const
     const int oy = center(th - ch), ox = center(tw - cw);
     const bool x4 = cw % 4 == 0 && tw % 4 == 0 && ox % 4 == 0 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(tiles) & 3u) == 0 &&
                     (reinterpret_cast<uintptr_t>(scene) & 3u) == 0;
-    if (x4) stitch_x4_kernel<<<simple_grid(total / 4), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W, oy, ox);
+    const bool x16 = cw % 16 == 0 && tw % 16 == 0 && ox % 16 == 0 && W % 16 == 0 && (reinterpret_cast<uintptr_t>(tiles) & 15u) == 0 &&
+                     (reinterpret_cast<uintptr_t>(scene) & 15u) == 0;
+    if (x16) {
+        const int rows = 4;      // rows per thread: four independent 128-bit loads in flight
+        const long long items = static_cast<long long>(n_tiles) * ((ch + rows - 1) / rows) * (cw / 16);
+        stitch_x16_kernel<<<simple_grid(items), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W, oy, ox, rows);
+    } else if (x4) stitch_x4_kernel<<<simple_grid(total / 4), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W, oy, ox);
     else stitch_kernel<<<simple_grid(total), kThreads, 0, stream>>>(tiles, n_tiles, th, tw, yx, ch, cw, scene, H, W, oy, ox);
     CVCS_CUDA_OK(cudaGetLastError());
     return CVCS_OK;
@@ -507,8 +593,9 @@ int vote_launch(const void* maps, int dtype, int n_maps, long long n, int C, voi
     CVCS_REQUIRE(out_dtype == CVCS_U8 || out_dtype == CVCS_I64, "cvcs_vote: out dtype tag %d", out_dtype);
     const int g = simple_grid(n);
     auto al4 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 3u) == 0; };
+    const bool wide = n % 16 == 0 && (reinterpret_cast<uintptr_t>(maps) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
     if (dtype == CVCS_U8 && out_dtype == CVCS_U8 && n_maps <= 8 && n % 4 == 0 && al4(maps) && al4(out) &&
-        try_vote_u8x4<1>(maps, n_maps, n, out, stream, simple_grid(n / 4))) {
+        try_vote_u8x4<1>(maps, n_maps, n, out, stream, wide)) {
         CVCS_CUDA_OK(cudaGetLastError());
         return CVCS_OK;
     }

@@ -104,7 +104,11 @@ enum cvcs_option {
     CVCS_OPT_PDL = 7,        /* K1 (TMA variant) launches with programmatic stream serialization (its prologue overlaps
                                 the tail of the previous kernel in the stream; the kernel waits for that kernel before
                                 it reads global memory, so results never change): 0 = default (on), 1 = on, 2 = off   */
-    CVCS_OPT_COUNT = 8
+    CVCS_OPT_L2_HINT = 8,    /* K1 (TMA variant) L2 eviction hints on its bulk copies: 0 = default (when a launch also stages
+                                the next batch's labels they are kept in L2 for the next launch, which then reads them from
+                                L2 instead of HBM); v in 1..8 = bit mask v - 1 (1 labels as above, 2 logits evict_first,
+                                4 gradient stores evict_first); 1 = no hints                                              */
+    CVCS_OPT_COUNT = 9
 };
 int cvcs_set_option(int option, int value);
 

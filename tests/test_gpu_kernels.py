@@ -241,6 +241,19 @@ def test_stitch_vector_path_with_center_crop():
     assert np.array_equal(out.cpu().numpy(), c_oracle.stitch(tiles.numpy(), yx.numpy(), H, W, crop=(ch, ch)))
 
 
+@pytest.mark.parametrize("th,ch", [(64, 64), (64, 32), (48, 16), (32, 22)])
+def test_stitch_16_pixel_path(th, ch):
+    """The 128-bit stitch path (crop, offset, widths multiples of 16): tiles on the grid, off the 16-pixel grid, partly
+    and wholly outside the scene, ch not a multiple of the rows a thread walks — all equal to the oracle."""
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(th * 100 + ch)
+    H, W = 300, 416                                   # the placed crops never overlap (overlaps are write races by contract)
+    yx = torch.tensor([[0, 0], [0, 64], [64, 128], [128, 192], [-16, 272], [280, -16], [71, 19], [150, 333], [900, 0], [200, 400]], dtype=torch.int32)
+    tiles = torch.randint(1, 16, (yx.shape[0], th, th), generator=g, dtype=torch.uint8)
+    out = ops.stitch(tiles.to(DEV), yx.to(DEV), (H, W), crop_hw=(ch, ch))
+    assert np.array_equal(out.cpu().numpy(), c_oracle.stitch(tiles.numpy(), yx.numpy(), H, W, crop=(ch, ch)))
+
+
 @pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
 @pytest.mark.parametrize("dtype,label_dtype", [(torch.float32, torch.uint8), (torch.float32, torch.int64), (torch.bfloat16, torch.uint8)])
 @pytest.mark.parametrize("C,H,W", [(7, 64, 128), (16, 48, 80), (20, 32, 64), (5, 37, 41)])
