@@ -309,8 +309,19 @@ struct HistCounter<2> {
 // SUB: sub-chunks of kThreads*VECP pixels per stage.  A consumer thread handles VECP consecutive pixels of every
 // sub-chunk, so SUB > 1 doubles the bytes per bulk copy and halves the per-stage bookkeeping per pixel without
 // widening the thread's register working set.
+// Register budget: two gradient CTAs per SM (96 registers) or three forward-only ones (64).  The one shape whose thread
+// holds more live values than that — NHWC bf16 with an 8-pixel span (C = 7: 56 logits, their labels, arg-maxima and
+// target gradients) — spilled 328 bytes per thread at 96 registers and ran at 0.46 of the copy peak; those kernels are
+// compiled for one CTA per SM (two forward-only) instead, and launch() reads the kernel's register count and sizes the
+// stages for what can be resident.
+template <typename T, int VECP, int C, bool NHWC, bool GRAD>
+constexpr int min_ctas_per_sm() {
+    constexpr bool wide = NHWC && sizeof(T) == 2 && VECP * C >= 48;
+    return GRAD ? (wide ? 1 : 2) : (wide ? 2 : 3);
+}
+
 template <typename T, int C, int VECP, bool NHWC, bool PRIV, bool GRAD, bool LOSS = true, int SUB = 1>
-__global__ void __launch_bounds__(kBlock, GRAD ? 2 : 3) ce_tma_kernel(const CeParams p, const Geom g) {
+__global__ void __launch_bounds__(kBlock, min_ctas_per_sm<T, VECP, C, NHWC, GRAD>()) ce_tma_kernel(const CeParams p, const Geom g) {
     constexpr int P = kThreads * VECP * SUB;
     constexpr int ES = sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
@@ -892,11 +903,15 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     // static shared memory of the chosen kernel (barriers, descriptors, weight tables, reduction scratch): it counts
     // against the SM's 228 KB like the dynamic part does
     static thread_local int static_smem[3] = {-1, -1, -1};
+    static thread_local int reg_ctas[3] = {1, 1, 1};       // CTAs per SM the kernel's register count allows
     const int kslot = p.dlogits ? 0 : (p.no_loss ? 1 : 2);
     if (static_smem[kslot] < 0) {
         cudaFuncAttributes fa;
         CVCS_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
         static_smem[kslot] = static_cast<int>(fa.sharedSizeBytes);
+        const int regs = ((fa.numRegs + 7) / 8) * 8;
+        reg_ctas[kslot] = regs > 0 ? 65536 / (regs * kBlock) : 1;
+        if (reg_ctas[kslot] < 1) reg_ctas[kslot] = 1;
     }
     const int reserve = 1024 + ((static_smem[kslot] + 255) / 256) * 256;   // 1 KB per CTA taken by the system + static
     int target_ctas = get_option(CVCS_OPT_TMA_CTAS);
@@ -904,6 +919,7 @@ int launch(const CeParams& p0, cudaStream_t stream, bool* handled) {
     if (!ctas_forced) {
         if (grad) target_ctas = ((233472 / 2 - reserve - g.stage_off) / g.stage_bytes >= 3) ? 2 : 1;
         else target_ctas = ((233472 / 3 - reserve - g.stage_off) / g.stage_bytes >= 3) ? 3 : 2;  // forward-only kernels fit 3 CTAs (64 regs)
+        if (target_ctas > reg_ctas[kslot]) target_ctas = reg_ctas[kslot];
     }
     const int per_cta = 233472 / target_ctas - reserve;  // 228 KB per SM
     int stages = (per_cta - g.stage_off) / g.stage_bytes;

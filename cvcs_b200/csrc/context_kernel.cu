@@ -36,53 +36,79 @@ constexpr int kWX = 3 * kBX + 2, kWY = 3 * kBY + 2;   // input window (one extra
 __global__ void __launch_bounds__(kThreads) context_kernel(const unsigned char* __restrict__ scene, int Cb, int H, int W,
                                                            const int* __restrict__ tile_yx, const int* __restrict__ tile_slot,
                                                            int p, unsigned char* __restrict__ out, const Taps taps_arg) {
+    // Every tap loop below runs the full five taps: rows with fewer carry zero weights, and adding x * 0 (x a byte or
+    // a finite partial sum, never negative) leaves the float32 sum bit-identical.  The window therefore keeps two
+    // spare columns and the horizontal result one spare (zero) row for the taps that fall past the end.
     __shared__ unsigned char win[kWY][kWX + 2];
-    __shared__ float hbuf[kWY][kBX];
-    __shared__ Taps taps;                      // indexed by row type at run time: shared memory, not a local-memory copy
-    if (threadIdx.x == 0) taps = taps_arg;
+    __shared__ float hbuf[kWY + 1][kBX];
+    __shared__ float wts[3][5];                 // indexed by row type at run time
+    __shared__ int offs[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 15) {
+        const int row = tid / 5, k = tid % 5;
+        wts[row][k] = k < taps_arg.n[row] ? taps_arg.w[row][k] : 0.f;
+    }
+    if (tid < 3) offs[tid] = taps_arg.off[tid];
+    if (tid < kBX) hbuf[kWY][tid] = 0.f;
     const int bx = blockIdx.x * kBX, by = blockIdx.y * kBY;     // output block origin inside the tile
     const int tile = blockIdx.z / Cb, band = blockIdx.z % Cb;
     const int slot = tile_slot ? tile_slot[tile] : tile;
     // crop origin in scene coordinates: (tly - p, tlx - p); window origin inside the crop: 3*b - 1
-    const long long cy0 = static_cast<long long>(tile_yx[2 * tile]) - p, cx0 = static_cast<long long>(tile_yx[2 * tile + 1]) - p;
+    const int cy0 = tile_yx[2 * tile] - p, cx0 = tile_yx[2 * tile + 1] - p;
     const int wy0 = 3 * by - 1, wx0 = 3 * bx - 1;
     const unsigned char* __restrict__ plane = scene + static_cast<size_t>(band) * H * W;
-    for (int r = threadIdx.x >> 5; r < kWY; r += kThreads / 32) {
-        const int yy = wy0 + r;                                    // row inside the 3p x 3p crop
-        const long long sy = cy0 + yy;
-        const bool row_ok = yy >= 0 && yy < 3 * p && sy >= 0 && sy < H;
-        const unsigned char* __restrict__ src = plane + (row_ok ? sy : 0) * W;
-        for (int c = threadIdx.x & 31; c < kWX; c += 32) {
-            const int xx = wx0 + c;
-            const long long sx = cx0 + xx;
-            win[r][c] = (row_ok && xx >= 0 && xx < 3 * p && sx >= 0 && sx < W) ? src[sx] : static_cast<unsigned char>(0);
+    {
+        // a lane owns window columns lane, lane + 32, ...: their validity is decided once, not once per row
+        constexpr int kCols = (kWX + 31) / 32;
+        bool cok[kCols];
+#pragma unroll
+        for (int j = 0; j < kCols; ++j) {
+            const int c = lane + 32 * j, xx = wx0 + c, sx = cx0 + xx;
+            cok[j] = c < kWX && xx >= 0 && xx < 3 * p && sx >= 0 && sx < W;
+        }
+        for (int r = warp; r < kWY; r += kThreads / 32) {
+            const int yy = wy0 + r, sy = cy0 + yy;                 // row inside the 3p x 3p crop / the scene
+            const bool row_ok = yy >= 0 && yy < 3 * p && sy >= 0 && sy < H;
+            const unsigned char* __restrict__ src = plane + static_cast<long long>(row_ok ? sy : 0) * W + (cx0 + wx0);
+#pragma unroll
+            for (int j = 0; j < kCols; ++j) {
+                const int c = lane + 32 * j;
+                if (c < kWX) win[r][c] = (row_ok && cok[j]) ? src[c] : static_cast<unsigned char>(0);
+            }
         }
     }
     __syncthreads();
-    // horizontal pass: output column x of the block reads window columns 3*x + off + 1 ...
-    for (int i = threadIdx.x; i < kWY * kBX; i += kThreads) {
-        const int r = i / kBX, x = i - r * kBX;
-        const int ox = bx + x;
-        float acc = 0.f;
-        if (ox < p) {
-            const int row = ox == 0 ? 0 : (ox == p - 1 ? 2 : 1);
-            const int c0 = 3 * x + taps.off[row] + 1;
-            acc = __fmul_rn(static_cast<float>(win[r][c0]), taps.w[row][0]);
-            for (int k = 1; k < taps.n[row]; ++k) acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(win[r][c0 + k]), taps.w[row][k]));
+    {
+        // horizontal pass: a thread keeps ONE output column (kThreads is a multiple of kBX), so its row type, first
+        // window column and weights are fixed; it walks down the window rows
+        const int x = tid % kBX, ox = bx + x;
+        const int row = ox == 0 ? 0 : (ox == p - 1 ? 2 : 1);
+        const int c0 = 3 * x + offs[row] + 1;
+        const float w0 = wts[row][0], w1 = wts[row][1], w2 = wts[row][2], w3 = wts[row][3], w4 = wts[row][4];
+        for (int r = tid / kBX; r < kWY; r += kThreads / kBX) {
+            const unsigned char* q = &win[r][c0];
+            float acc = __fmul_rn(static_cast<float>(q[0]), w0);
+            acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(q[1]), w1));
+            acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(q[2]), w2));
+            acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(q[3]), w3));
+            acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(q[4]), w4));
+            hbuf[r][x] = acc;
         }
-        hbuf[r][x] = acc;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kBY * kBX; i += kThreads) {
-        const int x = i % kBX, y = i / kBX;
-        const int ox = bx + x, oy = by + y;
-        if (ox < p && oy < p) {
-            const int row = oy == 0 ? 0 : (oy == p - 1 ? 2 : 1);
-            const int r0 = 3 * y + taps.off[row] + 1;
-            float acc = __fmul_rn(hbuf[r0][x], taps.w[row][0]);
-            for (int k = 1; k < taps.n[row]; ++k) acc = __fadd_rn(acc, __fmul_rn(hbuf[r0 + k][x], taps.w[row][k]));
-            const float r = rintf(acc);                       // torch.round: half to even
-            out[((static_cast<size_t>(slot) * Cb + band) * p + oy) * p + ox] = static_cast<unsigned char>(r < 0.f ? 0.f : (r > 255.f ? 255.f : r));
+    {
+        const int x = tid % kBX, ox = bx + x;
+        for (int y = tid / kBX; y < kBY; y += kThreads / kBX) {
+            const int oy = by + y;
+            if (ox < p && oy < p) {
+                const int row = oy == 0 ? 0 : (oy == p - 1 ? 2 : 1);
+                const int r0 = 3 * y + offs[row] + 1;
+                float acc = __fmul_rn(hbuf[r0][x], wts[row][0]);
+#pragma unroll
+                for (int k = 1; k < 5; ++k) acc = __fadd_rn(acc, __fmul_rn(hbuf[r0 + k][x], wts[row][k]));
+                const float r = rintf(acc);                       // torch.round: half to even
+                out[((static_cast<size_t>(slot) * Cb + band) * p + oy) * p + ox] = static_cast<unsigned char>(r < 0.f ? 0.f : (r > 255.f ? 255.f : r));
+            }
         }
     }
 }

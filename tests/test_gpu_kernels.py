@@ -94,6 +94,36 @@ def test_confmat(pd, td, C, ignore, n):
     assert int(st.item()) == 0
 
 
+@pytest.mark.parametrize("C,ignore", [(7, None), (7, 255), (7, 3), (8, 200), (15, 0), (16, 255), (16, None), (17, 255)])
+def test_confmat_u8_byte_parallel_path(C, ignore):
+    """u8 / u8 maps: words of four in-range pairs take the one-multiply key path (C <= 16), words holding an ignored
+    label, an out-of-range label or an out-of-range prediction the pixel path — mixed at every lane position, with runs
+    of identical pairs (the +4 update) — all equal to the oracle, and out-of-range pixels are counted in `status`."""
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(C * 7 + (ignore or 0))
+    n = 64 * 1024 + 7
+    t = torch.randint(0, C, (n,), generator=g, dtype=torch.uint8)
+    p = torch.randint(0, C, (n,), generator=g, dtype=torch.uint8)
+    t[4096:8192] = 2                                                   # long runs: whole words agree
+    p[4096:8192] = 1
+    p[6000:6100] = torch.randint(0, C, (100,), generator=g, dtype=torch.uint8)
+    if ignore is not None:
+        t[torch.rand(n, generator=g) < 0.05] = ignore
+    bad_t = torch.rand(n, generator=g) < 0.01
+    bad_p = torch.rand(n, generator=g) < 0.01
+    t[bad_t] = 250
+    p[bad_p] = 251
+    ref, n_bad = c_oracle.confmat(p.numpy(), t.numpy(), C, ignore)
+    cm = torch.zeros((C, C), dtype=torch.int64, device=DEV)
+    st = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ops.confmat_update(cm, p.to(DEV), t.to(DEV), C, ignore, status=st)
+    assert np.array_equal(cm.cpu().numpy(), ref)
+    assert int(st.item()) == int(n_bad)
+    cm.zero_()
+    ops.confmat_update(cm, p[1:].to(DEV)[:-2], t[1:].to(DEV)[:-2], C, ignore)   # contiguous copies, different phase
+    assert np.array_equal(cm.cpu().numpy(), c_oracle.confmat(p[1:-2].numpy(), t[1:-2].numpy(), C, ignore)[0])
+
+
 def test_confmat_flags_out_of_range():
     from cvcs_b200 import ops
     cm = torch.zeros((7, 7), dtype=torch.int64, device=DEV)
@@ -239,6 +269,21 @@ def test_stitch_vector_path_with_center_crop():
     yx = torch.tensor([[0, 0], [0, 24], [24, 48], [56, 80], [-8, 100], [72, -4]], dtype=torch.int32)
     out = ops.stitch(tiles.to(DEV), yx.to(DEV), (H, W), crop_hw=(ch, ch))
     assert np.array_equal(out.cpu().numpy(), c_oracle.stitch(tiles.numpy(), yx.numpy(), H, W, crop=(ch, ch)))
+
+
+@pytest.mark.parametrize("n,offset", [(4096, 0), (4099, 0), (3, 0), (4100, 1), (64, 4)])
+def test_colorize_paths(n, offset):
+    """iconvert (converters.py:23-36): the 4-pixel path (128-bit stores), its tail, the byte path for misaligned maps;
+    indices outside the table keep torch.ones' white."""
+    from cvcs_b200 import ops
+    g = torch.Generator().manual_seed(n + offset)
+    C = 16
+    lut = torch.rand(C, 3, generator=g)
+    base = torch.randint(0, C + 3, (n + offset,), generator=g, dtype=torch.uint8).to(DEV)
+    idx = base[offset:]                                                   # offset != 0: not 4-byte aligned
+    ref = c_oracle.colorize(idx.cpu().numpy(), lut.numpy())
+    assert np.array_equal(ops.colorize(idx, lut.to(DEV)).cpu().numpy(), ref)
+    assert np.array_equal(ops.colorize(idx.long(), lut.to(DEV)).cpu().numpy(), ref)
 
 
 @pytest.mark.parametrize("th,ch", [(64, 64), (64, 32), (48, 16), (32, 22)])
