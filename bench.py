@@ -378,7 +378,7 @@ def roofline_dict(ctx, achieved_gbs, bpp, px, k_ms, kernel, traffic_key, source,
 
 
 def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, label_dtype=None, layout="nchw",
-               per_launch_events=True, copy_ref=False, want_clocks=True, tw_mode="auto", label_block=32):
+               per_launch_events=True, copy_ref=False, want_clocks=True, tw_mode="auto", label_block=32, graph=False):
     """K1 on rotating buffer sets larger than L2.  When Σ v·w[y] is data dependent (class weights / ignore_index):
       tw_mode "chain"   a K4 launch one step ahead on a side stream (the next batch's labels are known while the current
                         K1 runs); at N > 1 followed by an NCCL all-reduce of the 8-byte sum
@@ -388,6 +388,10 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
                         (in its prologue, while its pipeline fills) and launch i+1 starts from that sum; across GPUs the
                         ranks' sums are exchanged inside K1.  One launch per step, one stream.
       tw_mode "auto"    "pipe" (u8 labels; int64 labels: "chain" on one GPU, "xchg" on several)
+    graph=True (stateless launch sequences only: constant Σw, no side stream, no per-launch events): the K timed steps
+    and the pass-end exchange are captured once into ONE CUDA graph and the timed region is one replay of it — the
+    first launch of a 20-step pass then starts ~10 us after the start event instead of after a Python call, and the
+    launches follow each other without the host in between.
     Returns a result dict."""
     torch, dist, ops, dev, world = ctx.torch, ctx.dist, ctx.ops, ctx.dev, ctx.world
     label_dtype = label_dtype or wl.get("label_dtype", "u8")
@@ -518,6 +522,20 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
         step(i, False, last=(i == warmup - 1))
     pass_end()                                                    # warm the pass-end collective up too
     ctx.fence(pre)
+    use_graph = bool(graph) and not prepass_on and not tw_pipe and not tw_kernel and not per_launch_events \
+        and not (world > 1 and ctx.args.nccl_pass_end)
+    cuda_graph = None
+    if use_graph:
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        cuda_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cuda_graph, stream=cap):
+            for i in range(steps):
+                step(i, False, last=(i == steps - 1))
+            pass_end()
+        torch.cuda.current_stream(dev).wait_stream(cap)
+        cuda_graph.replay()                                       # untimed: instantiation / upload costs land here
+        ctx.fence(pre)
     confmat.zero_()
     launches["n"] = 0
     issued["upto"] = -1
@@ -528,12 +546,17 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
     ctx.align_start()
     start.record()
     host_t0 = time.perf_counter()
-    for i in range(steps):
-        step(i, True, last=(i == steps - 1))
+    if cuda_graph is not None:
+        cuda_graph.replay()
+        launches["n"] = steps
+    else:
+        for i in range(steps):
+            step(i, True, last=(i == steps - 1))
     host_ms = (time.perf_counter() - host_t0) * 1e3 / steps     # enqueue cost; must stay below ms_per_step
     if pre is not None:
         torch.cuda.current_stream(dev).wait_stream(pre)
-    pass_end()
+    if cuda_graph is None:
+        pass_end()
     end.record()
     ctx.fence(pre)
     if want_clocks:
@@ -580,6 +603,8 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
                    "labels": label_dtype + (f" (blocky {label_block}x{label_block})" if label_block > 1 else " (i.i.d.)"), "grad": grad,
                    "metrics_only": metrics_only, "layout": layout,
                    "l2": f"inputs larger than L2: {n_sets} rotating sets of {set_bytes / 1e6:.0f} MB",
+                   "launch": (f"the {steps} steps" + (" + the pass-end exchange" if world > 1 else "") + " captured in one CUDA graph, replayed once in the timed region")
+                   if cuda_graph is not None else "one C-ABI call per step from Python on the current stream",
                    "total_weight": ("computed inside K1 (label pre-pass + grid barrier" + (", exchanged across ranks over NVLink inside the kernel)" if xchg is not None else ")"))
                    if tw_kernel else "pipelined across launches: K1 of step i sums the weights over step i+1's labels in its prologue" + (
                        "; the ranks' sums are exchanged inside K1 over NVLink peer memory" if xchg is not None else "") if tw_pipe
@@ -917,16 +942,16 @@ def run_secondary(ctx, names, steps, warmup):
                 wl = dict(WORKLOADS[nm])
                 kind = wl["kind"]
                 if kind == "ce":
-                    r = measure_ce(ctx, nm, wl, steps, warmup, want_clocks=False, per_launch_events=False)
+                    r = measure_ce(ctx, nm, wl, steps, warmup, want_clocks=False, per_launch_events=False, graph=bool(ctx.args.graph))
                 elif kind == "chain":
                     st = max(4, min(steps, 12)) if nm == "cfg5" else steps
                     r = measure_chain(ctx, nm, wl, st, min(warmup, 3), want_clocks=False)
                 else:
                     r = measure_tile(ctx, nm, wl, min(steps, 20), min(warmup, 3), want_clocks=False)
             elif nm == "eval_only":
-                r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, grad=False, want_clocks=False, per_launch_events=False)
+                r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, grad=False, want_clocks=False, per_launch_events=False, graph=bool(ctx.args.graph))
             elif nm == "metrics_only":
-                r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, metrics_only=True, want_clocks=False, per_launch_events=False)
+                r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, metrics_only=True, want_clocks=False, per_launch_events=False, graph=bool(ctx.args.graph))
             elif nm == "i64_labels":
                 r = measure_ce(ctx, "cfg2", dict(WORKLOADS["cfg2"]), steps, warmup, label_dtype="i64", want_clocks=False, per_launch_events=False)
             else:
@@ -971,6 +996,9 @@ def main():
                     help="1 (default, the library's default): K1 launches with programmatic stream serialization (its prologue overlaps "
                          "the previous kernel's tail); per-launch events would serialise the launches, so K1's average launch time "
                          "is then timed region / steps.  0: plain launches with CUDA events around every one")
+    ap.add_argument("--graph", type=int, default=1, choices=[0, 1],
+                    help="1 (default): a stateless step sequence (constant total weight) is captured in one CUDA graph and the timed "
+                         "region replays it; 0: one Python call per step")
     ap.add_argument("--l2-hint", type=int, default=0, help="A/B: K1 L2 eviction hints (CVCS_OPT_L2_HINT: 0 default, v = bit mask v - 1)")
     ap.add_argument("--label-block", type=int, default=32, help="side of the constant label blocks (1 = i.i.d. labels)")
     ap.add_argument("--tw-mode", default="auto", choices=["auto", "pipe", "kernel", "chain", "xchg"],
@@ -1014,7 +1042,7 @@ def main():
     else:
         res = measure_ce(ctx, args.workload, wl, args.steps, args.warmup, grad=grad, metrics_only=args.metrics_only,
                          label_dtype=label_dtype, layout=args.layout, per_launch_events=not args.pdl,
-                         copy_ref=not args.no_copy_ref, tw_mode=args.tw_mode, label_block=args.label_block)
+                         copy_ref=not args.no_copy_ref, tw_mode=args.tw_mode, label_block=args.label_block, graph=bool(args.graph))
     clocks = ctx.sampler.summary()
 
     e2e = e2e_eval = tcb = cpu = None

@@ -47,6 +47,7 @@ SIGNATURES = {
     "cvcs_last_error": (C.c_char_p, []),
     "cvcs_sm_count": (_i, []),
     "cvcs_workspace_bytes": (_sz, []),
+    "cvcs_stream_capture_id": (_i, [_vp, C.POINTER(C.c_ulonglong)]),
     "cvcs_set_option": (_i, [_i, _i]),
     "cvcs_label_hist": (_i, [_vp, _i, _ll, _i, _ll, _vp, _vp, _vp, _vp, _vp]),
     "cvcs_total_weight": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
@@ -110,3 +111,10 @@ def abi_version() -> int:
 
 def workspace_bytes() -> int:
     return int(lib.cvcs_workspace_bytes())
+
+
+def stream_capture_id(stream: int) -> int:
+    """Sequence number of the CUDA-graph capture the stream belongs to (0: not capturing)."""
+    out = C.c_ulonglong(0)
+    check(lib.cvcs_stream_capture_id(C.c_void_p(stream), C.byref(out)))
+    return int(out.value)

@@ -110,6 +110,15 @@ const char* cvcs_last_error(void) { return g_err; }
 int cvcs_sm_count(void) { return num_sms(); }
 size_t cvcs_workspace_bytes(void) { return kWorkspaceBytes; }
 
+int cvcs_stream_capture_id(void* stream, unsigned long long* id_out) {
+    CVCS_REQUIRE(id_out, "cvcs_stream_capture_id: NULL id_out");
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0ull;
+    CVCS_CUDA_OK(cudaStreamGetCaptureInfo(reinterpret_cast<cudaStream_t>(stream), &status, &id));
+    *id_out = status == cudaStreamCaptureStatusActive ? id : 0ull;
+    return CVCS_OK;
+}
+
 int cvcs_set_option(int option, int value) {
     CVCS_REQUIRE(option >= 0 && option < CVCS_OPT_COUNT, "cvcs_set_option: unknown option %d", option);
     g_options[option] = value;

@@ -32,14 +32,17 @@ struct Taps {
 
 constexpr int kBX = 32, kBY = 32;                // output block
 constexpr int kWX = 3 * kBX + 2, kWY = 3 * kBY + 2;   // input window (one extra tap each side)
+constexpr int kWinWords = (kWX + 3 + 3) / 4;          // 32-bit words per window row, whatever its byte phase (0..3)
+constexpr int kWinStride = 4 * kWinWords + 4;         // + the spare columns the zero-weight taps may touch
 
 __global__ void __launch_bounds__(kThreads) context_kernel(const unsigned char* __restrict__ scene, int Cb, int H, int W,
                                                            const int* __restrict__ tile_yx, const int* __restrict__ tile_slot,
-                                                           int p, unsigned char* __restrict__ out, const Taps taps_arg) {
+                                                           int p, unsigned char* __restrict__ out, const Taps taps_arg,
+                                                           const int words_ok) {
     // Every tap loop below runs the full five taps: rows with fewer carry zero weights, and adding x * 0 (x a byte or
     // a finite partial sum, never negative) leaves the float32 sum bit-identical.  The window therefore keeps two
     // spare columns and the horizontal result one spare (zero) row for the taps that fall past the end.
-    __shared__ unsigned char win[kWY][kWX + 2];
+    __shared__ __align__(16) unsigned char win[kWY][kWinStride];
     __shared__ float hbuf[kWY + 1][kBX];
     __shared__ float wts[3][5];                 // indexed by row type at run time
     __shared__ int offs[3];
@@ -57,8 +60,34 @@ __global__ void __launch_bounds__(kThreads) context_kernel(const unsigned char* 
     const int cy0 = tile_yx[2 * tile] - p, cx0 = tile_yx[2 * tile + 1] - p;
     const int wy0 = 3 * by - 1, wx0 = 3 * bx - 1;
     const unsigned char* __restrict__ plane = scene + static_cast<size_t>(band) * H * W;
-    {
-        // a lane owns window columns lane, lane + 32, ...: their validity is decided once, not once per row
+    // Window rows start at any byte phase of the scene row.  When every scene row is word aligned (W and H*W multiples
+    // of 4, aligned base — the usual case) a row is fetched as the 26 aligned 32-bit words that cover it, the bytes
+    // outside the scene or the crop masked to zero, and lands in shared memory at the same phase (`shift`); otherwise
+    // byte by byte.  Which bytes are valid does not depend on the row: decided once per lane.
+    int shift = 0;
+    if (words_ok) {
+        const int sx0 = cx0 + wx0;
+        shift = sx0 & 3;                                           // floor alignment, also for negative origins
+        const int xs = sx0 - shift + 4 * lane;                     // scene column of this lane's word
+        uint32_t mask = 0u;
+        if (lane < kWinWords) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int c = 4 * lane + b - shift, xx = wx0 + c, sx = xs + b;
+                if (c >= 0 && c < kWX && xx >= 0 && xx < 3 * p && sx >= 0 && sx < W) mask |= 0xffu << (8 * b);
+            }
+        }
+        for (int r = warp; r < kWY; r += kThreads / 32) {
+            const int yy = wy0 + r, sy = cy0 + yy;                 // row inside the 3p x 3p crop / the scene
+            const bool row_ok = yy >= 0 && yy < 3 * p && sy >= 0 && sy < H;
+            if (lane < kWinWords) {
+                uint32_t w = 0u;
+                if (row_ok && mask) w = __ldg(reinterpret_cast<const unsigned int*>(plane + static_cast<long long>(sy) * W + xs)) & mask;
+                reinterpret_cast<uint32_t*>(win[r])[lane] = w;
+            }
+        }
+    } else {
+        // a lane owns window columns lane, lane + 32, ...
         constexpr int kCols = (kWX + 31) / 32;
         bool cok[kCols];
 #pragma unroll
@@ -67,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) context_kernel(const unsigned char* 
             cok[j] = c < kWX && xx >= 0 && xx < 3 * p && sx >= 0 && sx < W;
         }
         for (int r = warp; r < kWY; r += kThreads / 32) {
-            const int yy = wy0 + r, sy = cy0 + yy;                 // row inside the 3p x 3p crop / the scene
+            const int yy = wy0 + r, sy = cy0 + yy;
             const bool row_ok = yy >= 0 && yy < 3 * p && sy >= 0 && sy < H;
             const unsigned char* __restrict__ src = plane + static_cast<long long>(row_ok ? sy : 0) * W + (cx0 + wx0);
 #pragma unroll
@@ -83,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) context_kernel(const unsigned char* 
         // window column and weights are fixed; it walks down the window rows
         const int x = tid % kBX, ox = bx + x;
         const int row = ox == 0 ? 0 : (ox == p - 1 ? 2 : 1);
-        const int c0 = 3 * x + offs[row] + 1;
+        const int c0 = 3 * x + offs[row] + 1 + shift;
         const float w0 = wts[row][0], w1 = wts[row][1], w2 = wts[row][2], w3 = wts[row][3], w4 = wts[row][4];
         for (int r = tid / kBX; r < kWY; r += kThreads / kBX) {
             const unsigned char* q = &win[r][c0];
@@ -162,7 +191,8 @@ int context_launch(const unsigned char* scene, int Cb, int H, int W, const int* 
         for (int j = 0; j < t.n[r]; ++j) t.w[r][j] = w[j];
     }
     dim3 grid((p + kBX - 1) / kBX, (p + kBY - 1) / kBY, n_tiles * Cb);
-    context_kernel<<<grid, kThreads, 0, stream>>>(scene, Cb, H, W, tile_yx, tile_slot, p, out, t);
+    const int words_ok = (W % 4 == 0 && (static_cast<long long>(H) * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(scene) & 3u) == 0) ? 1 : 0;
+    context_kernel<<<grid, kThreads, 0, stream>>>(scene, Cb, H, W, tile_yx, tile_slot, p, out, t, words_ok);
     CVCS_CUDA_OK(cudaGetLastError());
     return CVCS_OK;
 }

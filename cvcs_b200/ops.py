@@ -23,7 +23,7 @@ _DTYPE_TAG = {
 }
 
 _workspaces: dict = {}
-_capture_workspaces: collections.deque = collections.deque(maxlen=1024)   # see workspace()
+_capture_workspaces: "collections.OrderedDict" = collections.OrderedDict()   # see workspace()
 
 
 def _tag(t: torch.Tensor) -> int:
@@ -59,13 +59,21 @@ def _stream(dev: torch.device) -> int:
 def workspace(dev: torch.device) -> torch.Tensor:
     """Zero-initialised scratch buffer, one per (device, stream); kernels leave it zeroed.
 
-    While the current stream is being captured into a CUDA graph the buffer comes from the graph's own memory pool
-    (its zeroing becomes a memset node, so every replay starts from zeros) and is kept alive (the last 1024 of them,
-    128 KB each) instead of being cached per stream: the capture stream is reused by later captures, whose kernels must
-    not inherit a buffer that belongs to an earlier, possibly destroyed, graph."""
+    While the current stream is being captured into a CUDA graph the buffer comes from the graph's own memory pool (its
+    zeroing becomes a memset node, so every replay starts from zeros) and is shared by all the calls of THAT capture on
+    that stream — keyed by the capture's sequence number, because the capture stream is reused by later captures, whose
+    kernels must not inherit a buffer that belongs to an earlier, possibly destroyed, graph.  One memset node per graph:
+    consecutive K1 launches stay directly connected, so their programmatic overlap survives the capture.  The last 256
+    such buffers (128 KB each) are kept alive."""
     if torch.cuda.is_current_stream_capturing():
-        ws = torch.zeros(_lib.workspace_bytes(), dtype=torch.uint8, device=dev)
-        _capture_workspaces.append(ws)
+        stream = _stream(dev)
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream, _lib.stream_capture_id(stream))
+        ws = _capture_workspaces.get(key)
+        if ws is None:
+            ws = torch.zeros(_lib.workspace_bytes(), dtype=torch.uint8, device=dev)
+            _capture_workspaces[key] = ws
+            while len(_capture_workspaces) > 256:
+                _capture_workspaces.popitem(last=False)
         return ws
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev))
     ws = _workspaces.get(key)

@@ -86,6 +86,11 @@ int cvcs_sm_count(void);
  * be shared by all calls issued on one stream).  The buffer must be zero-filled ONCE after
  * allocation; kernels leave it zeroed again on exit. */
 size_t cvcs_workspace_bytes(void);
+/* Identity of the CUDA-graph capture `stream` is currently part of (cudaStreamGetCaptureInfo's sequence number, unique
+ * per capture in the process), 0 when the stream is not capturing.  Lets a host layer hand ONE zeroed workspace to all
+ * the calls of one captured graph (one memset node per graph instead of one per call, and no full dependency between
+ * consecutive K1 launches, which would undo their programmatic overlap). */
+int cvcs_stream_capture_id(void* stream, unsigned long long* id_out);
 
 /* Sizes: every index on the path is 64-bit.  Entry points accept up to 2^33 pixels per call (B*H*W, or n for the
  * index-map kernels) and any scene size; tests/test_gpu_large.py runs batches of 2.2e9 pixels / 4.4e9 logit elements

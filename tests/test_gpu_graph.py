@@ -128,3 +128,49 @@ def test_module_forward_backward_replay():
         ref_loss, ref_grad = torch_path.ce_loss_and_grad(x, y, w, 0)
         torch.testing.assert_close(loss_s.detach().cpu(), ref_loss, rtol=1e-5, atol=1e-7)
         torch.testing.assert_close(x_s.grad.cpu(), ref_grad, rtol=1e-5, atol=1e-8)
+
+
+def test_one_workspace_per_capture():
+    """All the calls captured into one graph share ONE zeroed workspace (keyed by the capture's sequence number): a single
+    memset node per graph, consecutive K1 launches directly connected.  Three K1 steps in one graph, replayed twice, give
+    the oracle's matrices and losses; a second capture on the same stream gets a workspace of its own."""
+    from cvcs_b200 import ops
+    B, C, H, W = 2, 7, 64, 64
+    batches = [_batch(20 + i, B, C, H, W) for i in range(3)]
+    xs = [x.to(DEV) for x, _ in batches]
+    ys = [y.to(DEV) for _, y in batches]
+    ds = [torch.zeros_like(x) for x in xs]
+    am = torch.zeros((B, H, W), dtype=torch.uint8, device=DEV)
+    cm = torch.zeros((C, C), dtype=torch.int64, device=DEV)
+    sums = torch.zeros((3, 3), dtype=torch.float64, device=DEV)
+    loss = torch.zeros(1, dtype=torch.float32, device=DEV)
+    inv = 1.0 / (B * H * W)
+
+    def steps():
+        for i in range(3):
+            ops.ce_fused(xs[i], ys[i], None, -100, want_grad=True, inv_total_weight=inv, dlogits=ds[i], argmax=am, confmat=cm,
+                         loss_sums=sums[i], loss_out=loss)
+
+    steps()
+    torch.cuda.synchronize()
+    before = len(ops._capture_workspaces)
+    g1 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g1):
+        steps()
+    assert len(ops._capture_workspaces) == before + 1
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        steps()
+    assert len(ops._capture_workspaces) == before + 2
+    cm.zero_()
+    cm_ref = torch.zeros((C, C), dtype=torch.int64)
+    for graph in (g1, g2, g1):
+        graph.replay()
+        torch.cuda.synchronize()
+        for i, (x, y) in enumerate(batches):
+            ref_loss, ref_grad = torch_path.ce_loss_and_grad(x, y, None, -100)
+            pred = torch.max(x, dim=1)[1]
+            cm_ref += torch.bincount(y.long().reshape(-1) * C + pred.reshape(-1), minlength=C * C).reshape(C, C)
+            torch.testing.assert_close(ds[i].cpu(), ref_grad, rtol=1e-5, atol=1e-8)
+            torch.testing.assert_close((sums[i, 0] / sums[i, 1]).float().cpu(), ref_loss, rtol=1e-5, atol=1e-7)
+        assert torch.equal(cm.cpu(), cm_ref)

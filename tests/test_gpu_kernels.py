@@ -273,8 +273,8 @@ def test_stitch_vector_path_with_center_crop():
 
 @pytest.mark.parametrize("n,offset", [(4096, 0), (4099, 0), (3, 0), (4100, 1), (64, 4)])
 def test_colorize_paths(n, offset):
-    """iconvert (converters.py:23-36): the 4-pixel path (128-bit stores), its tail, the byte path for misaligned maps;
-    indices outside the table keep torch.ones' white."""
+    """iconvert (converters.py:23-36) on u8 and int64 maps of odd lengths and alignments; indices outside the table
+    keep torch.ones' white."""
     from cvcs_b200 import ops
     g = torch.Generator().manual_seed(n + offset)
     C = 16
