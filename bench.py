@@ -522,9 +522,18 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
         step(i, False, last=(i == warmup - 1))
     pass_end()                                                    # warm the pass-end collective up too
     ctx.fence(pre)
-    use_graph = bool(graph) and not prepass_on and not tw_pipe and not tw_kernel and not per_launch_events \
-        and not (world > 1 and ctx.args.nccl_pass_end)
+    # pipelined Σw on ONE GPU is capturable too: the only state a replay needs is the first batch's sum, which an untimed
+    # K4 launch supplies before each replay (across GPUs the previous launch has also pre-published its successor's sum
+    # to the peers, which a replay would not match: those runs keep one call per step)
+    use_graph = bool(graph) and not prepass_on and not tw_kernel and not per_launch_events \
+        and not (tw_pipe and world > 1) and not (world > 1 and ctx.args.nccl_pass_end)
     cuda_graph = None
+    g0 = gstep["n"]
+
+    def prime():
+        if tw_pipe:
+            ops.label_hist(sets[g0 % n_sets][1], C, ii, weight=weight, total_weight_out=nxt[g0 % 2])
+
     if use_graph:
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))
@@ -534,8 +543,10 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
                 step(i, False, last=(i == steps - 1))
             pass_end()
         torch.cuda.current_stream(dev).wait_stream(cap)
+        prime()
         cuda_graph.replay()                                       # untimed: instantiation / upload costs land here
         ctx.fence(pre)
+        prime()
     confmat.zero_()
     launches["n"] = 0
     issued["upto"] = -1
