@@ -401,16 +401,23 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
     grad = grad and not metrics_only
     set_bytes = px_per_gpu * C * esize * (2 if grad else 1)
     n_sets = max(3, min(16, -(-400_000_000 // set_bytes)))     # rotate >= 400 MB (L2 is 126 MB) through the caches
+    ii = wl["ignore_index"]
+    data_dependent_tw = wl["weighted"] or (0 <= ii <= 255) or label_dtype == "i64"
+    if tw_mode == "auto":
+        tw_mode = "pipe" if label_dtype == "u8" else ("xchg" if world > 1 else "chain")
+    if graph and grad and data_dependent_tw and tw_mode == "pipe" and label_dtype == "u8" and world > 1:
+        # a replayed pass must end where it began (the last launch pre-publishes the first one's sum to the peers):
+        # rotate over a number of sets that divides the pass
+        for n in range(n_sets, 9):
+            if steps % n == 0:
+                n_sets = n
+                break
     sets, weight = synth_inputs(torch, wl, dev, seed=1234 + ctx.rank, n_sets=n_sets, label_dtype=label_dtype, layout=layout,
                                 block=label_block)
     dl = [torch.empty_like(x) for x, _ in sets] if grad else [None] * n_sets
     am = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in sets]
     confmat = torch.zeros((C, C), dtype=torch.int64, device=dev)
     loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
-    ii = wl["ignore_index"]
-    data_dependent_tw = wl["weighted"] or (0 <= ii <= 255) or label_dtype == "i64"
-    if tw_mode == "auto":
-        tw_mode = "pipe" if label_dtype == "u8" else ("xchg" if world > 1 else "chain")
     tw_kernel = grad and data_dependent_tw and tw_mode == "kernel" and label_dtype == "u8"
     tw_pipe = grad and data_dependent_tw and tw_mode == "pipe" and label_dtype == "u8"
     prepass_on = grad and data_dependent_tw and not tw_kernel and not tw_pipe
@@ -522,11 +529,11 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
         step(i, False, last=(i == warmup - 1))
     pass_end()                                                    # warm the pass-end collective up too
     ctx.fence(pre)
-    # pipelined Σw on ONE GPU is capturable too: the only state a replay needs is the first batch's sum, which an untimed
-    # K4 launch supplies before each replay (across GPUs the previous launch has also pre-published its successor's sum
-    # to the peers, which a replay would not match: those runs keep one call per step)
+    # pipelined Σw is capturable too: the only state a replay needs is the first batch's sum, which an untimed K4 launch
+    # supplies before each replay; across GPUs the previous launch has also pre-published its successor's sum to the
+    # peers, so the pass must be a whole number of rotations (and of the two-slot next-sum ring) to be replayed
     use_graph = bool(graph) and not prepass_on and not tw_kernel and not per_launch_events \
-        and not (tw_pipe and world > 1) and not (world > 1 and ctx.args.nccl_pass_end)
+        and not (tw_pipe and world > 1 and (steps % n_sets or steps % 2)) and not (world > 1 and ctx.args.nccl_pass_end)
     cuda_graph = None
     g0 = gstep["n"]
 
@@ -573,6 +580,16 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
     if want_clocks:
         ctx.sampler.stop()
     ms_total = start.elapsed_time(end)
+    tw_rel_err = None
+    if tw_pipe or tw_kernel or tw_xchg:
+        # the divisor the last timed launch used (its total_weight_out) against K4 over the same labels, summed over ranks
+        j_last = (gstep["n"] - 1) % n_sets if tw_pipe else (steps - 1) % n_sets
+        got = float((twg if tw_xchg else tws)[j_last][0].item())
+        exp = torch.zeros(2, dtype=torch.float64, device=dev)
+        ops.label_hist(sets[j_last][1], C, ii, weight=weight, total_weight_out=exp)
+        if world > 1:
+            dist.all_reduce(exp[0:1])
+        tw_rel_err = abs(got - float(exp[0].item())) / max(float(exp[0].item()), 1e-30)
     k1_ms = [a.elapsed_time(b) for a, b in k1_events] or [ms_total / steps]
     k1_avg = sum(k1_ms) / len(k1_ms)
     (ms_max,), table = ctx.max_over_ranks(ms_total)
@@ -609,7 +626,7 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
                                   "cvcs K1 eval_fused (metrics mode)", tkey, src,
                                   {"same_size_copy_gbs_in_this_harness": copy_gbs}),
         "gpu_launches": launches["n"], "host_enqueue_ms_per_step": host_ms, "per_rank": per_rank,
-        "check": {"confusion_total": int(confmat.sum().item()), "loss": float(loss_out.item())},
+        "check": {"confusion_total": int(confmat.sum().item()), "loss": float(loss_out.item()), "total_weight_rel_err": tw_rel_err},
         "config": {"per_gpu_batch": B, "classes": C, "tile": [H, W],
                    "labels": label_dtype + (f" (blocky {label_block}x{label_block})" if label_block > 1 else " (i.i.d.)"), "grad": grad,
                    "metrics_only": metrics_only, "layout": layout,
