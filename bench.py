@@ -541,19 +541,34 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
         if tw_pipe:
             ops.label_hist(sets[g0 % n_sets][1], C, ii, weight=weight, total_weight_out=nxt[g0 % 2])
 
+    graph_note = None
     if use_graph:
-        cap = torch.cuda.Stream(device=dev)
-        cap.wait_stream(torch.cuda.current_stream(dev))
-        cuda_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cuda_graph, stream=cap):
-            for i in range(steps):
-                step(i, False, last=(i == steps - 1))
-            pass_end()
-        torch.cuda.current_stream(dev).wait_stream(cap)
-        prime()
-        cuda_graph.replay()                                       # untimed: instantiation / upload costs land here
-        ctx.fence(pre)
-        prime()
+        g_before = gstep["n"]
+        try:
+            cap = torch.cuda.Stream(device=dev)
+            cap.wait_stream(torch.cuda.current_stream(dev))
+            cuda_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cuda_graph, stream=cap):
+                for i in range(steps):
+                    step(i, False, last=(i == steps - 1))
+                pass_end()
+            torch.cuda.current_stream(dev).wait_stream(cap)
+        except Exception as e:                                    # never lose the line to a capture problem: plain launches
+            cuda_graph = None
+            gstep["n"] = g_before
+            graph_note = f"graph capture failed ({type(e).__name__}); "
+            torch.cuda.synchronize(dev)
+        if world > 1:                                             # all ranks replay, or none does
+            ok = torch.tensor([1.0 if cuda_graph is not None else 0.0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) < 1.0:
+                cuda_graph = None
+                gstep["n"] = g_before
+        if cuda_graph is not None:
+            prime()
+            cuda_graph.replay()                                   # untimed: instantiation / upload costs land here
+            ctx.fence(pre)
+            prime()
     confmat.zero_()
     launches["n"] = 0
     issued["upto"] = -1
@@ -632,7 +647,7 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
                    "metrics_only": metrics_only, "layout": layout,
                    "l2": f"inputs larger than L2: {n_sets} rotating sets of {set_bytes / 1e6:.0f} MB",
                    "launch": (f"the {steps} steps" + (" + the pass-end exchange" if world > 1 else "") + " captured in one CUDA graph, replayed once in the timed region")
-                   if cuda_graph is not None else "one C-ABI call per step from Python on the current stream",
+                   if cuda_graph is not None else (graph_note or "") + "one C-ABI call per step from Python on the current stream",
                    "total_weight": ("computed inside K1 (label pre-pass + grid barrier" + (", exchanged across ranks over NVLink inside the kernel)" if xchg is not None else ")"))
                    if tw_kernel else "pipelined across launches: K1 of step i sums the weights over step i+1's labels in its prologue" + (
                        "; the ranks' sums are exchanged inside K1 over NVLink peer memory" if xchg is not None else "") if tw_pipe
