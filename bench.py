@@ -324,8 +324,18 @@ class Ctx:
         t0 = torch.tensor([time.time() + 0.0015], dtype=torch.float64, device=self.dev)
         self.dist.all_reduce(t0, op=self.dist.ReduceOp.MAX)
         target = float(t0.item())
+        if not self.args.nccl_pass_end:
+            # ... and the GPUs meet once more ON THE DEVICE: a one-element exchange over the peer-mapped region is a
+            # barrier kernel (every rank waits for every rank's flag).  It is enqueued in front of the start event, so the
+            # hosts have long queued the timed work when the kernels let go — the regions then start within microseconds
+            # of each other whatever the hosts' enqueue jitter.
+            if getattr(self, "_align_buf", None) is None:
+                self._align_buf = torch.zeros(1, dtype=torch.float64, device=self.dev)
+            xchg = self.exchange()
         while time.time() < target:
             pass
+        if not self.args.nccl_pass_end:
+            xchg.allreduce_(self._align_buf)
 
     def max_over_ranks(self, *vals):
         """Element-wise max over ranks of a few host floats (device-timed regions are compared on the device)."""
