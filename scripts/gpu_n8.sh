@@ -17,5 +17,5 @@ for f in sorted(glob.glob('gpurun_out/bench_*.log')):
     print(f.split('/')[-1], 'value', round(d['value'], 2), 'ms/step', round(d['ms_per_step'], 4), 'frac', d.get('roofline') and round(d['roofline']['frac'], 3),
           'check', d.get('check'), d['config'].get('launch', '')[:40], d.get('per_rank'))
     for k, v in (d.get('secondary') or {}).items():
-        print('     ', k, v.get('value') and round(v['value'], 2), v.get('roofline', {}).get('frac') and round(v['roofline']['frac'], 3), v.get('check'), v.get('error', ''))
+        print('     ', k, v.get('value') and round(v['value'], 2), v.get('roofline', {}).get('frac') and round(v['roofline']['frac'], 3), v.get('check'), v.get('per_rank'), v.get('error', ''))
 PY
