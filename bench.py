@@ -54,6 +54,10 @@ WORKLOADS = {
                      desc="20-class head alone, fp32 logits, batch 16 per GPU"),
     "c16": dict(kind="ce", B=16, C=16, H=1024, W=1024, dtype="f32", weighted=False, ignore_index=-100,
                 desc="16 classes (what utils.py:77-78 hard-codes), fp32 logits, batch 16 of 1024x1024"),
+    "c32": dict(kind="ce", B=4, C=32, H=1024, W=1024, dtype="f32", weighted=False, ignore_index=-100,
+                desc="32 classes (beyond the register-resident range C <= 21: the generic one-pixel-per-thread kernel), fp32, batch 4"),
+    "c64": dict(kind="ce", B=4, C=64, H=1024, W=1024, dtype="f32", weighted=False, ignore_index=-100,
+                desc="64 classes (generic kernel), fp32 logits, batch 4 of 1024x1024"),
     "ref": dict(kind="ce", B=10, C=16, H=224, W=224, dtype="f32", weighted=False, ignore_index=0, label_dtype="i64",
                 desc="the reference's own training shape (configs/train/server.yaml:23-36): batch 10 of 224x224, 16 classes, "
                      "int64 labels, ignore_index 0"),
