@@ -1,6 +1,7 @@
 // ce_fused.cu — K1 entry: argument validation and variant selection.
 //   tma     : warp-specialised, cp.async.bulk-staged (ce_tma_impl.cuh) — primary path
 //   direct  : register-resident 128-bit LDG/STG, NCHW (ce_direct.cu)
+//   wide    : C > 21, NCHW: bulk-copy staged, a thread walks its pixel's classes in shared memory (ce_wide.cu)
 //   generic : any C <= 1024 / any layout, one pixel per thread (ce_direct.cu)
 // cvcs_set_option(CVCS_OPT_CE_PATH, ...) forces a variant for A/B measurements and path-coverage
 // tests (all are CUDA; there is no CPU path).
@@ -13,6 +14,17 @@ namespace cvcs {
 
 int ce_tma_launch_f32(const CeParams& p, int layout, cudaStream_t stream, bool* handled);
 int ce_tma_launch_bf16(const CeParams& p, int layout, cudaStream_t stream, bool* handled);
+int ce_wide_launch(const CeParams& p, int logits_dtype, cudaStream_t stream, bool* handled);   // ce_wide.cu: C > kMaxRegC, NCHW
+
+// C beyond the register-resident range: the shared-memory class walk (same bulk-copy pipeline), when the layout and
+// alignment allow bulk copies; *handled = false leaves the call to the generic kernel
+static int try_wide(const CeParams& p, int logits_dtype, int layout, bool ptr16, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    const int forced = get_option(CVCS_OPT_CE_PATH);
+    if (forced == 2 || forced == 3 || p.C <= kMaxRegC || layout != CVCS_NCHW || !ptr16 || p.hw % 16 != 0 || p.tw_mode != 0)
+        return CVCS_OK;
+    return ce_wide_launch(p, logits_dtype, stream, handled);
+}
 
 int label_hist_launch(const void*, int, long long, int, long long, unsigned long long*, const float*, double*, void*,
                       cudaStream_t);
@@ -65,6 +77,8 @@ static int tw_fallback(CeParams p, int logits_dtype, int layout, int target_dtyp
             }
         }
     }
+    rc = try_wide(p, logits_dtype, layout, ptr16, stream, &handled);
+    if (handled || rc) return rc;
     return ce_generic_launch(p, logits_dtype, layout, stream);
 }
 
@@ -167,6 +181,8 @@ int ce_fused_launch(const void* logits, int logits_dtype, int layout, const void
         }
     }
     (void)esize;
+    rc = try_wide(p, logits_dtype, layout, ptr16, stream, &handled);
+    if (handled || rc) return rc;
     return ce_generic_launch(p, logits_dtype, layout, stream);
 }
 

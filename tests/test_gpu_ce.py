@@ -289,3 +289,73 @@ def test_full_size_properties(lib, dtype, C, B):
     g0 = (x0.grad * inv).numpy()
     gt = d[:1].float().cpu().numpy()
     assert np.abs(gt - g0).max() <= (F32_TOL if dtype == torch.float32 else BF16_TOL) * np.abs(g0).max()
+
+
+# ---- class counts beyond the register-resident range: the shared-memory class walk (csrc/ce_wide.cu) ----------------
+@pytest.mark.parametrize("dtype,label_dtype", [(torch.float32, torch.uint8), (torch.float32, torch.int64), (torch.bfloat16, torch.uint8)])
+@pytest.mark.parametrize("C,H,W,weighted,ignore", [(22, 48, 80, False, -100), (32, 64, 64, True, 255), (40, 16, 48, True, 3),
+                                                    (64, 48, 48, False, 255), (100, 32, 32, True, -100)])
+def test_wide_class_counts(lib, dtype, label_dtype, C, H, W, weighted, ignore):
+    """C > 21, NCHW, H*W % 16 == 0: chunks of 256 / 512 pixels with a ragged last chunk per image, weights, ignored
+    labels, out-of-range labels excluded here (see the status test), NaN / inf rows and ties.  Against the oracle at the
+    path's tolerance, and bit for bit against the generic one-pixel-per-thread kernel (same arithmetic, term for term)."""
+    g = torch.Generator().manual_seed(C * 1000 + H + W)
+    B = 3
+    x = (torch.randn(B, C, H, W, generator=g) * 3).to(dtype).float()
+    x[0, :, 0, :8] = 1.0                                        # ties -> first index
+    x[0, 5, 1, :4] = float("nan")                               # NaN is maximal, first NaN wins
+    x[1, 7, 2, :3] = float("inf")
+    x[2, :, 3, :2] = float("-inf")
+    t = torch.randint(0, C, (B, H, W), generator=g)
+    if 0 <= ignore:
+        t[torch.rand(B, H, W, generator=g) < 0.1] = ignore
+    w = (torch.rand(C, generator=g) + 0.5).numpy() if weighted else None
+    tol = F32_TOL if dtype == torch.float32 else BF16_TOL
+    res = {}
+    for path in ("auto", "generic"):
+        lib.set_option(lib.OPT_CE_PATH, PATHS[path])
+        res[path] = run_k1(x.numpy(), t.numpy(), w, ignore, dtype=dtype, label_dtype=label_dtype,
+                           argmax_dtype=torch.uint8 if label_dtype == torch.uint8 else torch.int64)
+        res[path + "/fwd"] = run_k1(x.numpy(), t.numpy(), w, ignore, want_grad=False, dtype=dtype, label_dtype=label_dtype)
+    loss, sums, grad, am, cm = res["auto"]
+    clean = np.isfinite(x.numpy()).all(axis=1)                   # the gradient comparison skips the rows with NaN / inf
+    xs, ts = x.numpy().copy(), t.numpy().copy()
+    am_ref = c_oracle.argmax(xs)
+    assert np.array_equal(am, am_ref)
+    cm_ref, _ = c_oracle.confmat(am_ref, ts, C, ignore if 0 <= ignore else None)
+    assert np.array_equal(cm, cm_ref)
+    # bit-identical to the generic kernel: gradients, argmax, matrix — with and without gradients (the f64 loss sums
+    # are folded in a different pixel order: equal to rounding)
+    for a, b in ((res["auto"], res["generic"]), (res["auto/fwd"], res["generic/fwd"])):
+        np.testing.assert_allclose(a[1], b[1], rtol=1e-12, equal_nan=True)
+        assert (a[2] is None and b[2] is None) or np.array_equal(a[2], b[2], equal_nan=True)
+        assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    assert np.array_equal(res["auto/fwd"][3], am_ref) and np.array_equal(res["auto/fwd"][4], cm_ref)
+    # finite rows against the oracle's fp64 gradient: per-pixel gradients of clean pixels do not depend on the others
+    # except through 1/Σw, which both sides take from the same labels
+    l2, s2, g2 = c_oracle.cross_entropy(xs, ts, w, ignore)
+    mask = np.broadcast_to(clean[:, None], g2.shape)
+    scale = max(np.abs(g2[mask]).max(), 1e-30)
+    assert np.abs(grad[mask] - g2[mask]).max() <= tol * scale
+
+
+def test_wide_metrics_mode_and_status(lib):
+    """cvcs_eval_fused (no loss) and the out-of-range label count on the wide path."""
+    from cvcs_b200 import ops
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 2, 48, 32, 48
+    x = torch.randn(B, C, H, W, generator=g)
+    t = torch.randint(0, C, (B, H, W), generator=g, dtype=torch.uint8)
+    t[0, 0, :5] = 200                                           # out of range, not the ignore value
+    t[1, 1, :7] = 255
+    am = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
+    ops.eval_fused(x.to(dev), t.to(dev), 255, argmax=am, confmat=cm)
+    am_ref = c_oracle.argmax(x.numpy())
+    keep = (t.numpy() < C)
+    cm_ref, _ = c_oracle.confmat(am_ref[keep], t.numpy()[keep], C, 255)
+    assert np.array_equal(am.cpu().numpy().astype(np.int64), am_ref)
+    assert np.array_equal(cm.cpu().numpy(), cm_ref)
+    loss, sums, _ = ops.ce_fused(x.to(dev), t.to(dev), None, 255, want_grad=False)
+    assert int(sums[2].item()) == 5 and np.isnan(float(loss.item()))     # torch would raise; the loss is poisoned
