@@ -51,7 +51,7 @@ __device__ __forceinline__ WideChunk wide_chunk_of(const CeParams& p, int P, lon
 }
 
 template <typename T, bool GRAD>
-__global__ void __launch_bounds__(kBlock, 1) ce_wide_kernel(const CeParams p, const WideGeom g) {
+__global__ void __launch_bounds__(kBlock, 2) ce_wide_kernel(const CeParams p, const WideGeom g) {
     constexpr int ES = sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[3 * kMaxStages];  // full[S], done[S], free[S]
@@ -175,25 +175,57 @@ __global__ void __launch_bounds__(kBlock, 1) ce_wide_kernel(const CeParams p, co
             }
             const bool valid = static_cast<unsigned int>(tv) < static_cast<unsigned int>(C);
             bad += (!valid && tv != -1) ? 1u : 0u;
-            // ---- walk 1: max (for the shift) and torch's argmax (first maximum, NaN is maximal)
-            float best = lds_elem<T>(col, 0), m = best;
+            // ---- walk 1: max (for the shift) and first-max index.  x * 0 summed over the row is NaN exactly when the row
+            // holds a NaN or an infinity: those rows (rare) redo the walk with torch's NaN-is-maximal rule and take the
+            // recomputing form of walks 2 / 3 below, which is the generic kernel's arithmetic on the original logits
+            float best = lds_elem<T>(col, 0);
             int arg = 0;
+            float chk = best * 0.f;
 #pragma unroll 4
             for (int c = 1; c < C; ++c) {
                 const float x = lds_elem<T>(col + static_cast<size_t>(c) * plane, 0);
-                if (better(x, best)) {
+                chk = fmaf(x, 0.f, chk);
+                if (x > best) {
                     best = x;
                     arg = c;
                 }
-                m = fmaxf(m, x);
+            }
+            float m = best;
+            const bool special = chk != chk;
+            if (special) {
+                best = lds_elem<T>(col, 0);
+                m = best;
+                arg = 0;
+                for (int c = 1; c < C; ++c) {
+                    const float x = lds_elem<T>(col + static_cast<size_t>(c) * plane, 0);
+                    if (better(x, best)) {
+                        best = x;
+                        arg = c;
+                    }
+                    m = fmaxf(m, x);
+                }
             }
             if (do_loss) {
-                // ---- walk 2: Σ exp(x - m), in class order
-                float s = 0.f;
-#pragma unroll 4
-                for (int c = 0; c < C; ++c) s += ex2_ftz((lds_elem<T>(col + static_cast<size_t>(c) * plane, 0) - m) * kLog2e);
                 const float xt = valid ? lds_elem<T>(col + static_cast<size_t>(tv) * plane, 0) : 0.f;
                 const float w = valid ? wsm[tv] : 0.f;
+                // fp32 with gradients: walk 2 leaves exp(x - m) in place of x, walk 3 only scales it (the value the
+                // recomputing form would produce, bit for bit, with one MUFU and four instructions fewer per element);
+                // bf16 keeps its logits until walk 3, because a bf16 copy of exp(x - m) would be rounded twice
+                const bool in_place = GRAD && ES == 4 && !special;
+                // ---- walk 2: Σ exp(x - m), in class order
+                float s = 0.f;
+                if (in_place) {
+#pragma unroll 4
+                    for (int c = 0; c < C; ++c) {
+                        unsigned char* e = col + static_cast<size_t>(c) * plane;
+                        const float v = ex2_ftz((lds_elem<T>(e, 0) - m) * kLog2e);
+                        s += v;
+                        sts_elem<T>(e, 0, v);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int c = 0; c < C; ++c) s += ex2_ftz((lds_elem<T>(col + static_cast<size_t>(c) * plane, 0) - m) * kLog2e);
+                }
                 const float nll = fmaf(lg2_ftz(s), kLn2, m - xt);
                 lsum += valid ? static_cast<double>(w * nll) : 0.0;
                 wsum += static_cast<double>(w);
@@ -202,10 +234,18 @@ __global__ void __launch_bounds__(kBlock, 1) ce_wide_kernel(const CeParams p, co
                     const float gsc = valid ? w * inv_tw : 0.f;      // exact zeros at ignored pixels
                     const float r = gsc * rcp_ftz(s);
                     const float gt = fmaf(ex2_ftz((xt - m) * kLog2e), r, -gsc);
+                    if (in_place) {
 #pragma unroll 4
-                    for (int c = 0; c < C; ++c) {
-                        unsigned char* e = col + static_cast<size_t>(c) * plane;
-                        sts_elem<T>(e, 0, fmaf(ex2_ftz((lds_elem<T>(e, 0) - m) * kLog2e), r, 0.f));
+                        for (int c = 0; c < C; ++c) {
+                            unsigned char* e = col + static_cast<size_t>(c) * plane;
+                            sts_elem<T>(e, 0, fmaf(lds_elem<T>(e, 0), r, 0.f));
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int c = 0; c < C; ++c) {
+                            unsigned char* e = col + static_cast<size_t>(c) * plane;
+                            sts_elem<T>(e, 0, fmaf(ex2_ftz((lds_elem<T>(e, 0) - m) * kLog2e), r, 0.f));
+                        }
                     }
                     if (valid) sts_elem<T>(col + static_cast<size_t>(tv) * plane, 0, gt);
                 }
@@ -238,33 +278,37 @@ int launch_wide(const CeParams& p0, cudaStream_t stream, bool* handled) {
         CVCS_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
         static_smem[grad] = static_cast<int>(fa.sharedSizeBytes);
     }
-    const int budget = 227 * 1024 - static_smem[grad] - 256;
+    // Geometry: the consumers are issue / latency limited (three walks of dependent shared-memory accesses), so two CTAs
+    // per SM — 16 consumer warps — come first whenever three stages of 256 pixels fit in half an SM's shared memory;
+    // otherwise one CTA with 512- or 256-pixel stages.  The C x C bins give way first (fewer replicas).
+    const int budget_full = 227 * 1024 - static_smem[grad] - 256;
+    const int budget_half = 233472 / 2 - 1024 - static_smem[grad] - 256;
     WideGeom g{};
     const int wsm_bytes = ((C * 4 + 127) / 128) * 128;
     bool found = false;
-    const int min_stages_try[2] = {3, 2};
-    for (int t = 0; t < 2 && !found; ++t) {
-        for (int P = 512; P >= 256 && !found; P >>= 1) {
-            int reps = p.confmat ? shared_bin_replicas(C * C, 32 * 1024, 64 * 1024) : 0;
-            for (;;) {
-                const int hist = p.confmat ? ((C * C * (reps > 0 ? reps : 0) * 4 + 127) / 128) * 128 : 0;
-                const int stage_bytes = ((C * P * ES + P * tsize + 127) / 128) * 128;
-                const int stages = (budget - hist - wsm_bytes) / stage_bytes;
-                if (stages >= min_stages_try[t]) {
-                    g.P = P;
-                    g.stage_bytes = stage_bytes;
-                    g.label_off = C * P * ES;
-                    g.wsm_off = hist;
-                    g.stage_off = hist + wsm_bytes;
-                    g.conf_reps = reps;
-                    g.stages = stages > 4 ? 4 : stages;
-                    found = true;
-                    break;
-                }
-                if (reps <= 1) break;
-                reps >>= 1;
+    struct Try { int budget, P, min_stages; };
+    const Try tries[] = {{budget_half, 256, 3}, {budget_full, 512, 3}, {budget_full, 256, 3}, {budget_full, 512, 2}, {budget_full, 256, 2}};
+    for (const Try& t : tries) {
+        int reps = p.confmat ? shared_bin_replicas(C * C, 32 * 1024, 64 * 1024) : 0;
+        for (;;) {
+            const int hist = p.confmat ? ((C * C * reps * 4 + 127) / 128) * 128 : 0;
+            const int stage_bytes = ((C * t.P * ES + t.P * tsize + 127) / 128) * 128;
+            const int stages = (t.budget - hist - wsm_bytes) / stage_bytes;
+            if (stages >= t.min_stages) {
+                g.P = t.P;
+                g.stage_bytes = stage_bytes;
+                g.label_off = C * t.P * ES;
+                g.wsm_off = hist;
+                g.stage_off = hist + wsm_bytes;
+                g.conf_reps = reps;
+                g.stages = stages > 4 ? 4 : stages;
+                found = true;
+                break;
             }
+            if (reps <= 1) break;
+            reps >>= 1;
         }
+        if (found) break;
     }
     if (!found) {
         *handled = false;          // a single class-plane stage does not fit twice: the generic kernel takes it
