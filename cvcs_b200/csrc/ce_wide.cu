@@ -81,57 +81,80 @@ __global__ void __launch_bounds__(kBlock, 2) ce_wide_kernel(const CeParams p, co
     unsigned int bad = 0;
 
     if (tid >= kThreads) {
+        // ================= producers: warp 8 loads, warp 9 stores — ALL lanes issue =================
+        // A stage here is C bulk copies of a class-plane row (1-2 KB each), not the 8 copies of 4 KB of the register
+        // kernels: one issuing lane cannot keep up (measured: ~80 cycles per copy, C = 32 forward-only stuck at 0.57
+        // of the copy peak).  Lane l issues rows l, l + 32, ...; lane 0 does the waiting, the chunk claim and the
+        // barrier arrivals, and the warp moves in step (__syncwarp).  Bulk async-groups are per thread, so every
+        // storing lane commits and waits for its own group before lane 0 hands the stage back.
         const T* __restrict__ logits = reinterpret_cast<const T*>(p.logits);
         T* __restrict__ dlogits = reinterpret_cast<T*>(p.dlogits);
         const unsigned char* __restrict__ target = reinterpret_cast<const unsigned char*>(p.target);
-        if (tid == kThreads) {
-            // ---- loader
+        const int lane = tid & 31;
+        if (tid < kThreads + 32) {
+            // ---- loader warp
             Ring ring{0, 0u};
-            long long q = blockIdx.x;
+            unsigned int q = blockIdx.x;
             for (long long i = 0;; ++i) {
-                if (i >= S) {
+                if (i >= S && lane == 0) {
                     const uint32_t prev = ring.phase ^ 1u;
                     if constexpr (GRAD) mbar_wait<true>(bar0 + 8 * (2 * kMaxStages + ring.s), prev);
                     else mbar_wait<true>(bar0 + 8 * (kMaxStages + ring.s), prev);
                 }
+                __syncwarp();
                 const uint32_t bar = bar0 + 8 * ring.s;
-                if (q >= n_chunks) {
-                    desc[ring.s].n = -1;
-                    mbar_arrive(bar);
+                if (static_cast<long long>(q) >= n_chunks) {
+                    if (lane == 0) {
+                        desc[ring.s].n = -1;
+                        mbar_arrive(bar);
+                    }
                     break;
                 }
                 const WideChunk ck = wide_chunk_of(p, P, q);
-                desc[ring.s] = ck;
                 const uint32_t dst = stage0 + ring.s * g.stage_bytes;
                 const uint32_t row = static_cast<uint32_t>(ck.n) * ES;
                 const uint32_t lbytes = static_cast<uint32_t>(ck.n) * tsize;
-                mbar_expect_tx(bar, row * C + lbytes);
-                for (int c = 0; c < C; ++c) bulk_g2s(dst + c * P * ES, logits + ck.elem0 + c * p.hw, row, bar);
-                bulk_g2s(dst + g.label_off, target + ck.pix0 * tsize, lbytes, bar);
-                q = static_cast<long long>(gridDim.x) + atomicAdd(&p.ws->next_chunk, 1u);
+                if (lane == 0) {
+                    desc[ring.s] = ck;
+                    mbar_expect_tx(bar, row * C + lbytes);          // release: publishes desc
+                }
+                __syncwarp();
+                for (int c = lane; c < C; c += 32) bulk_g2s(dst + c * P * ES, logits + ck.elem0 + c * p.hw, row, bar);
+                unsigned int qn = 0u;
+                if (lane == 0) {
+                    bulk_g2s(dst + g.label_off, target + ck.pix0 * tsize, lbytes, bar);
+                    qn = gridDim.x + atomicAdd(&p.ws->next_chunk, 1u);
+                }
+                q = __shfl_sync(0xffffffffu, qn, 0);
                 ring.next(S);
             }
-        } else if (GRAD && tid == kThreads + 32) {
-            // ---- storer
+        } else if (GRAD) {
+            // ---- storer warp
             Ring ring{0, 0u};
             int pending = -1;
             for (;;) {
                 const uint32_t done = bar0 + 8 * (kMaxStages + ring.s);
-                if (pending >= 0 && !mbar_test(done, ring.phase)) {
+                int early = 0;
+                if (lane == 0) early = (pending >= 0 && !mbar_test(done, ring.phase)) ? 1 : 0;
+                early = __shfl_sync(0xffffffffu, early, 0);
+                if (early) {
                     bulk_wait_read<0>();
-                    mbar_arrive(bar0 + 8 * (2 * kMaxStages + pending));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar0 + 8 * (2 * kMaxStages + pending));
                     pending = -1;
                 }
-                mbar_wait<true>(done, ring.phase);
+                if (lane == 0) mbar_wait<true>(done, ring.phase);
+                __syncwarp();
                 const WideChunk ck = desc[ring.s];
                 if (ck.n < 0) break;
                 const uint32_t src = stage0 + ring.s * g.stage_bytes;
                 const uint32_t row = static_cast<uint32_t>(ck.n) * ES;
-                for (int c = 0; c < C; ++c) bulk_s2g(dlogits + ck.elem0 + c * p.hw, src + c * P * ES, row);
+                for (int c = lane; c < C; c += 32) bulk_s2g(dlogits + ck.elem0 + c * p.hw, src + c * P * ES, row);
                 bulk_commit();
                 if (pending >= 0) {
-                    bulk_wait_read<1>();
-                    mbar_arrive(bar0 + 8 * (2 * kMaxStages + pending));
+                    bulk_wait_read<1>();                               // this lane's older group has left shared memory
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar0 + 8 * (2 * kMaxStages + pending));
                 }
                 pending = ring.s;
                 ring.next(S);
