@@ -99,7 +99,7 @@ int cvcs_stream_capture_id(void* stream, unsigned long long* id_out);
 /* Process-wide tuning knobs (A/B measurements, path-coverage tests).  Every value selects
  * among CUDA implementations of the same entry point; none changes results. */
 enum cvcs_option {
-    CVCS_OPT_CE_PATH = 0,    /* cvcs_ce_fused variant: 0 auto, 1 TMA-staged, 2 direct-load, 3 generic */
+    CVCS_OPT_CE_PATH = 0,    /* cvcs_ce_fused variant: 0 auto, 1 TMA-staged (incl. the wide-C form, C > 21), 2 direct-load, 3 generic */
     CVCS_OPT_TMA_STAGES = 1, /* TMA-staged variant: pipeline depth (0 = as many as fit, max 8)        */
     CVCS_OPT_TMA_WAIT_HINT = 2, /* 0: mbarrier waits pass a long suspend-time hint (default), 1: no hint */
     CVCS_OPT_TMA_VECP = 3,   /* NCHW, C <= 8: pixels per consumer thread (0 = default; f32: 2|4, bf16: 4|8) */
