@@ -113,7 +113,8 @@ def cpu_model() -> str:
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (NVML, ~5 ms period)."""
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, ~1 ms period: the driver's 20-step region lasts
+    3 ms)."""
 
     def __init__(self, index: int):
         self.index, self.samples, self.reasons = index, [], set()
@@ -145,7 +146,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.001)
 
     def start(self):
         if self.ok:
