@@ -599,7 +599,7 @@ def measure_ce(ctx, name, wl, steps, warmup, *, grad=True, metrics_only=False, l
     host_t0 = time.perf_counter()
     if cuda_graph is not None:
         cuda_graph.replay()
-        launches["n"] = steps
+        launches["n"] = steps + (1 if world > 1 else 0)            # K1 per step (+ the pass-end exchange kernel)
     else:
         for i in range(steps):
             step(i, True, last=(i == steps - 1))
